@@ -1,0 +1,95 @@
+"""Load a tests/golden/*.npz fixture: rebuild its seeded inputs, check their sha256, hand back
+the reference's outputs (see oracle/gen_golden.py for how they were made)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+
+from d3fields_b200 import scene as S
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+CASES = ['cfg1', 'mixed4v', 'odd3v', 'ties', 'batch3chunks']
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _points(meta, blob):
+    how = meta['pts_how']
+    if 'in.pts' in blob:
+        return blob['in.pts']
+    if how == 'config_points:cfg1':
+        return S.config_points('cfg1')
+    if how.startswith('grid30+'):
+        sc = S.make_scene(4, 480, 640, seed=1)
+        return np.concatenate([S.grid_points(30, 30, 30), S.scattered_points(12000, 1), S.adversarial_points(sc, 3)])
+    if how == 'grid52x50x50':
+        return S.grid_points(52, 50, 50)
+    raise KeyError(how)
+
+
+class Golden:
+    def __init__(self, name):
+        blob = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz')))
+        self.meta = json.loads(bytes(blob['meta']).decode())
+        self.blob = blob
+        mk = self.meta['make']
+        if mk == 'tie_scene':
+            from oracle.gen_golden import tie_scene
+            self.scene = tie_scene()
+        else:
+            self.scene = S.make_scene(mk['V'], mk['H'], mk['W'], seed=mk['seed'],
+                                      feat=tuple(mk['feat']) if mk['feat'] else None,
+                                      num_inst=mk['num_inst'], color=mk['color'])
+        if 'in.pts' in blob:
+            self.pts = blob['in.pts']
+        elif name == 'odd3v':
+            self.pts = np.concatenate([S.grid_points(17, 13, 11), S.scattered_points(3001, 2),
+                                       S.adversarial_points(self.scene, 5, 16)])
+        else:
+            self.pts = _points(self.meta, blob)
+        self.pts = np.ascontiguousarray(self.pts, dtype=np.float32)
+        self.rows = blob['rows']
+        self.names = self.meta['names']
+        self.mu = self.meta['mu']
+        sha = self.meta['input_sha256']
+        got = {'pts': _sha(self.pts), 'pose': _sha(self.scene.pose), 'K': _sha(self.scene.K),
+               'depth': _sha(self.scene.depth), **{k: _sha(v) for k, v in self.scene.maps.items()}}
+        bad = [k for k in sha if got.get(k) != sha[k]]
+        assert not bad, f'golden {name}: regenerated inputs differ from the pinned ones: {bad}'
+
+    # -- comparisons ------------------------------------------------------------------------
+    def check_exact(self, key, arr):
+        """dist / valid_mask (and eval_dist variants): bit-exact against the reference's bytes."""
+        ref_sha = self.meta['output_sha256'][key]
+        want_dtype = np.bool_ if 'valid' in key else np.float32
+        a = np.ascontiguousarray(np.asarray(arr).astype(want_dtype, copy=False))
+        if _sha(a) == ref_sha:
+            return
+        stored = self.blob['out.' + key]
+        full = bool(self.blob['full.' + key])
+        got = a if full else a[self.rows]
+        if a.dtype == np.float32:
+            nbad = int((got.view(np.uint32) != stored.view(np.uint32)).sum())
+        else:
+            nbad = int((got != stored).sum())
+        raise AssertionError(f'{key}: sha256 differs from the reference; {nbad} mismatches among the '
+                             f'{"full" if full else "stored"} rows')
+
+    def check_close(self, key, arr, rtol=1e-4, atol_scale=2e-6):
+        """(N,C) or (V,N,C) float outputs: |a-b| <= rtol*|b| + atol_scale*max|b| on the stored rows,
+        and the float64 sum / abs-sum checksums over the full array to the same relative accuracy."""
+        a = np.asarray(arr, dtype=np.float32)
+        ref = self.blob['out.' + key]
+        got = a[:, self.rows] if key.endswith('_inter') else a[self.rows]
+        assert got.shape == ref.shape, (key, got.shape, ref.shape)
+        scale = float(np.abs(ref).max()) if ref.size else 0.0
+        err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+        tol = rtol * np.abs(ref) + atol_scale * scale
+        assert (err <= tol).all(), f'{key}: max err {err.max():.3e}, worst excess {(err - tol).max():.3e}'
+        s, sa = self.meta['checksum'][key]
+        a64 = a.astype(np.float64)
+        assert abs(a64.sum() - s) <= rtol * max(sa, 1e-30) * 1e-2 + 1e-9, (key, a64.sum(), s)
+        assert abs(np.abs(a64).sum() - sa) <= rtol * max(sa, 1e-30), (key, np.abs(a64).sum(), sa)

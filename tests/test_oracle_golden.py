@@ -1,0 +1,45 @@
+"""CPU: the oracle restatement (oracle/field_oracle.py) against the golden vectors produced by the
+unmodified reference (oracle/gen_golden.py).  This is what pins the oracle; everything on the
+GPU box is then compared with the oracle and with the same fixtures."""
+import numpy as np
+import pytest
+
+from golden_util import CASES, Golden
+from oracle import field_oracle as O
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_numpy_oracle_matches_reference_golden(name):
+    g = Golden(name)
+    sc = g.scene
+    inter = not g.meta['batch']
+    out = O.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, g.names, mu=g.mu,
+                       return_inter=inter)
+    g.check_exact('dist', out['dist'])
+    g.check_exact('valid_mask', out['valid_mask'])
+    for k in g.names:
+        g.check_close(k, out[k])
+        if inter:
+            g.check_close(k + '_inter', out[k + '_inter'])
+    od = O.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, mu=g.mu, eval_dist=True)
+    g.check_exact('evaldist.dist', od['dist'])
+    g.check_exact('evaldist.valid_mask', od['valid_mask'])
+
+
+def test_oracle_empty_and_single_point():
+    g = Golden('ties')
+    sc = g.scene
+    out = O.field_eval(np.zeros((0, 3), np.float32), sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, ['dino_feats'])
+    assert out['dist'].shape == (0,) and out['valid_mask'].shape == (0,) and out['dino_feats'].shape[0] == 0
+    one = O.field_eval(g.pts[:1], sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, ['dino_feats'])
+    full = O.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, ['dino_feats'])
+    assert np.array_equal(one['dino_feats'][0], full['dino_feats'][0])
+
+
+def test_uint8_mask_is_read_as_its_float_value():
+    g = Golden('odd3v')
+    sc = g.scene
+    m8 = {'mask': sc.maps['mask'].astype(np.uint8)}
+    a = O.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, m8, ['mask'], mu=g.mu)
+    b = O.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, ['mask'], mu=g.mu)
+    assert np.array_equal(a['mask'], b['mask'])
