@@ -1,0 +1,144 @@
+"""ctypes binding of libd3f.so (include/d3f.h).  Plain pointers and sizes only.
+
+There is no fallback: if the library is missing or cannot be loaded, every entry point raises
+NativeLibraryError — the field query never runs on anything but the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+from . import build as _build
+
+D3F_MAX_VIEWS = 16
+D3F_MAX_KEYS = 8
+D3F_F32, D3F_U8 = 0, 1
+FLAG_EVAL_DIST, FLAG_RECIP_NORM = 1, 2
+ABI_VERSION = 1
+
+# every symbol include/d3f.h declares (tests check the built library exports exactly these)
+SYMBOLS = ('d3f_eval', 'd3f_eval_host', 'd3f_pca_project', 'd3f_create_grid', 'd3f_abi_version',
+           'd3f_last_error', 'd3f_launch_count', 'd3f_last_variant')
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class D3FError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f'libd3f error {code}: {msg}')
+        self.code = code
+
+
+class D3FObs(C.Structure):
+    _fields_ = [('V', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('pose', C.c_void_p), ('K', C.c_void_p), ('depth', C.c_void_p)]
+
+
+class D3FKey(C.Structure):
+    _fields_ = [('data', C.c_void_p), ('dtype', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('C', C.c_int32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return os.environ.get('D3F_LIBRARY', _build.LIB_PATH)
+
+
+def load() -> C.CDLL:
+    """Load libd3f.so (building it first if sources are present and it is stale or missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if 'D3F_LIBRARY' not in os.environ and not _build.is_current():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box: use a prebuilt library if there is one
+            if not os.path.exists(path):
+                raise NativeLibraryError(f'libd3f.so is not built and cannot be built here: {e}') from e
+    if not os.path.exists(path):
+        raise NativeLibraryError(f'{path} does not exist; run `python -m d3fields_b200.build`')
+    try:
+        lib = C.CDLL(path)
+    except OSError as e:
+        raise NativeLibraryError(f'cannot load {path}: {e}') from e
+    vp, i32, i64, u32, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float, C.c_double
+    lib.d3f_eval.argtypes = [C.POINTER(D3FObs), vp, i64, C.POINTER(D3FKey), i32, vp, vp,
+                             C.POINTER(vp), C.POINTER(vp), u32, f32, vp]
+    lib.d3f_eval.restype = C.c_int
+    lib.d3f_eval_host.argtypes = [C.POINTER(D3FObs), vp, i64, C.POINTER(D3FKey), i32, vp, vp,
+                                  C.POINTER(vp), u32, f32]
+    lib.d3f_eval_host.restype = C.c_int
+    lib.d3f_pca_project.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp]
+    lib.d3f_pca_project.restype = C.c_int
+    lib.d3f_create_grid.argtypes = [f64, f64, f64, f64, i32, i32, i32, vp, vp]
+    lib.d3f_create_grid.restype = C.c_int
+    lib.d3f_abi_version.restype = C.c_int
+    lib.d3f_last_error.restype = C.c_char_p
+    lib.d3f_launch_count.restype = C.c_int64
+    lib.d3f_last_variant.argtypes = [i32]
+    lib.d3f_last_variant.restype = C.c_char_p
+    got = lib.d3f_abi_version()
+    if got != ABI_VERSION:
+        raise NativeLibraryError(f'{path}: ABI version {got}, this package expects {ABI_VERSION}')
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise D3FError(rc, load().d3f_last_error().decode(errors='replace'))
+
+
+def _ptr_array(ptrs: Sequence[Optional[int]]):
+    arr = (C.c_void_p * max(len(ptrs), 1))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def _keys_array(keys: Sequence[tuple]):
+    arr = (D3FKey * max(len(keys), 1))()
+    for i, (data, dtype, h, w, c) in enumerate(keys):
+        arr[i] = D3FKey(data, dtype, h, w, c)
+    return arr
+
+
+def eval_device(V: int, H: int, W: int, pose: int, K: int, depth: int, pts: int, n: int,
+                keys: Sequence[tuple], dist: int, valid: int, outs: Sequence[int],
+                inters: Optional[Sequence[Optional[int]]], flags: int, mu: float, stream: int) -> None:
+    """d3f_eval with raw device addresses.  keys: (data_ptr, dtype, h, w, C) tuples."""
+    lib = load()
+    obs = D3FObs(V, H, W, pose, K, depth)
+    inter_arr = _ptr_array(inters) if inters is not None else None
+    _check(lib.d3f_eval(C.byref(obs), pts, n, _keys_array(keys), len(keys), dist, valid,
+                        _ptr_array(outs), inter_arr, flags, mu, stream))
+
+
+def eval_host(V: int, H: int, W: int, pose: int, K: int, depth: int, pts_host: int, n: int,
+              keys: Sequence[tuple], dist_host: int, valid_host: int, outs_host: Sequence[int],
+              flags: int, mu: float) -> None:
+    lib = load()
+    obs = D3FObs(V, H, W, pose, K, depth)
+    _check(lib.d3f_eval_host(C.byref(obs), pts_host, n, _keys_array(keys), len(keys), dist_host, valid_host,
+                             _ptr_array(outs_host), flags, mu))
+
+
+def pca_project(x: int, n: int, c: int, mean: int, comp: int, n_comp: int, y: int, stream: int) -> None:
+    _check(load().d3f_pca_project(x, n, c, mean, comp, n_comp, y, stream))
+
+
+def create_grid(x0: float, y0: float, z0: float, step: float, nx: int, ny: int, nz: int, pts: int, stream: int) -> None:
+    _check(load().d3f_create_grid(x0, y0, z0, step, nx, ny, nz, pts, stream))
+
+
+def launch_count() -> int:
+    return int(load().d3f_launch_count())
+
+
+def last_variant(k: int = 0) -> str:
+    return load().d3f_last_variant(k).decode()

@@ -1,0 +1,313 @@
+"""Drop-in mirror of the reference's field-query interface, backed by libd3f.so.
+
+Mirrors, for the hot path only, what reference fusion.py exposes and its drivers import
+(`from fusion import Fusion, create_init_grid`, reference vis_repr.py:13):
+
+  create_init_grid(boundaries, step_size)              reference fusion.py:79-88
+  project_points_coords(pts, Rt, K)                    reference fusion.py:32-55   (thin view over eval's kernel)
+  Fusion(num_cam, feat_backbone, device, dtype)        reference fusion.py:203
+  Fusion.update(obs)                                   reference fusion.py:686-714
+  Fusion.eval(pts, return_names, return_inter)         reference fusion.py:305-394
+  Fusion.eval_dist(pts)                                reference fusion.py:396-436
+  Fusion.batch_eval(pts, return_names)                 reference fusion.py:526-545
+  Fusion.text_queries_for_inst_mask(_no_track)(...)    reference fusion.py:1173 / :1112 (delegated, see below)
+  Fusion.get_inst_num()                                reference fusion.py:1258
+  Fusion.curr_obs_torch                                reference fusion.py:210-215, 707-714
+
+Same names, argument meaning, return dict and error behaviour.  What differs:
+
+  * eval/eval_dist/batch_eval launch hand-written sm_100a kernels through the C ABI
+    (include/d3f.h); torch only owns the device memory and the stream.  There is no CPU
+    fallback: without the library or a CUDA device the call raises.
+  * The perception front-end (DINOv2 / GroundingDINO / SAM / XMem, reference fusion.py:223-286)
+    is out of scope.  update() takes precomputed features
+    (obs['dino_feats']) or a user-supplied `feature_extractor`; the mask methods delegate to a
+    user-supplied `perception` object, and set_instance_masks() injects masks directly.
+  * 'mask' may be stored as uint8 one-hot (4x less traffic); outputs are float32 either way.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+
+
+def create_init_grid(boundaries, step_size):
+    """Voxel-centre grid over `boundaries`, z fastest; returns (coords (N,3) f32 on CPU, grid shape).
+    Same construction as reference fusion.py:79-88 (torch.arange in float32, + step/2, ij meshgrid)."""
+    axes = []
+    for a in ('x', 'y', 'z'):
+        lo, hi = boundaries[a + '_lower'], boundaries[a + '_upper']
+        axes.append(torch.arange(lo, hi, step_size, dtype=torch.float32) + step_size / 2)
+    gx, gy, gz = torch.meshgrid(*axes, indexing='ij')
+    return torch.stack([gx, gy, gz], dim=-1).reshape(-1, 3), gx.shape
+
+
+def _as_device(t, device, dtype=None):
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(t)
+    return t.to(device=device, dtype=dtype) if dtype is not None else t.to(device=device)
+
+
+class Fusion:
+    """The per-frame multi-view field (reference fusion.py:202) with a CUDA-native query path."""
+
+    def __init__(self, num_cam, feat_backbone='dinov2', device='cuda:0', dtype=torch.float32,
+                 feature_extractor: Optional[Callable] = None, perception=None):
+        if dtype != torch.float32:
+            raise ValueError('the field query computes in float32 (the reference default, fusion.py:203)')
+        self.device = device
+        self.dtype = dtype
+        self.num_cam = num_cam
+        self.feat_backbone = feat_backbone
+        self.mu = 0.02                       # reference fusion.py:208
+        self.curr_obs_torch: Dict[str, object] = {}
+        self.H = self.W = -1
+        self.feature_extractor = feature_extractor
+        self.perception = perception
+        self.index_rounding = 'cpu'          # 'cpu' (parity oracle) | 'cuda' (torch CUDA kernels' rounding)
+
+    # ------------------------------------------------------------------ state ------------
+    def update(self, obs):
+        """obs: 'color' (V,H,W,3) uint8, 'depth' (V,H,W), 'pose' (V,3,4) world->camera, 'K' (V,3,3);
+        optionally 'dino_feats' (V,h,w,C) precomputed.  Layout written: reference fusion.py:707-714."""
+        depth = obs['depth']
+        self.num_cam = int(depth.shape[0])
+        color = obs.get('color')
+        if 'dino_feats' in obs:
+            feats = _as_device(obs['dino_feats'], self.device, self.dtype).contiguous()
+        elif self.feature_extractor is not None:
+            params = {'patch_h': color.shape[1] // 10, 'patch_w': color.shape[2] // 10}   # fusion.py:694-697
+            feats = _as_device(self.feature_extractor(color, params), self.device, self.dtype).contiguous()
+        else:
+            feats = None
+        if feats is not None:
+            self.curr_obs_torch['dino_feats'] = feats
+        if color is not None:
+            self.curr_obs_torch['color'] = color
+            self.curr_obs_torch['color_tensor'] = (_as_device(color, self.device, self.dtype) / 255.0).contiguous()
+        pose = _as_device(obs['pose'], self.device, self.dtype)
+        if pose.shape[-2:] == (4, 4):
+            pose = pose[:, :3]
+        self.curr_obs_torch['depth'] = _as_device(depth, self.device, self.dtype).contiguous()
+        self.curr_obs_torch['pose'] = pose.contiguous()
+        self.curr_obs_torch['K'] = _as_device(obs['K'], self.device, self.dtype).contiguous()
+        _, self.H, self.W = depth.shape
+
+    def set_instance_masks(self, masks, labels: Optional[Sequence[str]] = None, as_uint8: bool = False):
+        """Write curr_obs_torch['mask'] directly: `masks` is a (V,H,W) uint8 label image or a
+        (V,H,W,num_inst) one-hot (reference layout, fusion.py:1171).  Stands in for the
+        Grounded-SAM/XMem front-end on synthetic or precomputed masks."""
+        m = _as_device(masks, self.device)
+        if m.dim() == 3:
+            num = int(m.max().item()) + 1 if labels is None else len(labels)
+            m = (m.unsqueeze(-1) == torch.arange(num, device=m.device, dtype=m.dtype))
+        m = m.to(torch.uint8 if as_uint8 else self.dtype).contiguous()
+        self.curr_obs_torch['mask'] = m
+        if labels is not None:
+            self.curr_obs_torch['consensus_mask_label'] = list(labels)
+
+    def get_inst_num(self):
+        return self.curr_obs_torch['mask'].shape[-1]          # reference fusion.py:1258-1259
+
+    def text_queries_for_inst_mask_no_track(self, queries, thresholds, boundaries, use_sam=False,
+                                            merge_all=False, expected_labels=None, robot_pcd=None, **kw):
+        return self._perceive('text_queries_for_inst_mask_no_track', queries, thresholds, boundaries,
+                              use_sam=use_sam, merge_all=merge_all, expected_labels=expected_labels,
+                              robot_pcd=robot_pcd, **kw)
+
+    def text_queries_for_inst_mask(self, queries, thresholds, boundaries, use_sam=False,
+                                   merge_all=False, expected_labels=None, robot_pcd=None, **kw):
+        return self._perceive('text_queries_for_inst_mask', queries, thresholds, boundaries,
+                              use_sam=use_sam, merge_all=merge_all, expected_labels=expected_labels,
+                              robot_pcd=robot_pcd, **kw)
+
+    def _perceive(self, method, *a, **kw):
+        if self.perception is None:
+            raise RuntimeError(
+                f'{method}: the Grounded-SAM / XMem front-end is outside this package (SURVEY.md §2 rows 10-12); '
+                'pass perception=<object with this method> to Fusion(...), or call set_instance_masks()')
+        masks, labels = getattr(self.perception, method)(self, *a, **kw)
+        self.set_instance_masks(masks, labels)
+
+    # ------------------------------------------------------------------ query ------------
+    def _check_pts(self, pts):
+        if len(self.curr_obs_torch) == 0:           # reference fusion.py:313-317
+            print('Please call update() first!')
+            exit()
+        assert type(pts) == torch.Tensor            # reference fusion.py:318-320
+        assert len(pts.shape) == 2
+        assert pts.shape[1] == 3
+        if pts.dtype != torch.float32:
+            raise ValueError(f'pts must be float32, got {pts.dtype}')
+
+    def _obs_ptrs(self):
+        o = self.curr_obs_torch
+        depth, pose, K = o['depth'], o['pose'], o['K']
+        for name, t in (('depth', depth), ('pose', pose), ('K', K)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError(f"curr_obs_torch['{name}'] must be a contiguous float32 CUDA tensor")
+        V, H, W = depth.shape
+        if tuple(pose.shape) != (V, 3, 4) or tuple(K.shape) != (V, 3, 3):
+            raise ValueError(f'pose/K shapes {tuple(pose.shape)}/{tuple(K.shape)} do not match depth {tuple(depth.shape)}')
+        if (H, W) != (self.H, self.W):
+            raise ValueError(f'depth is {H}x{W} but Fusion.H/W = {self.H}x{self.W}')
+        return V, H, W, pose.data_ptr(), K.data_ptr(), depth.data_ptr()
+
+    def _key_tuple(self, name, V):
+        vol = self.curr_obs_torch[name]              # KeyError for unknown names, as in the reference (fusion.py:373)
+        if not isinstance(vol, torch.Tensor) or vol.dim() != 4 or vol.shape[0] != V:
+            raise ValueError(f"curr_obs_torch['{name}'] must be a (V,h,w,C) tensor")
+        if vol.dtype == torch.bool:
+            vol = vol.view(torch.uint8)
+        if vol.dtype not in (torch.float32, torch.uint8):
+            raise ValueError(f"curr_obs_torch['{name}'] must be float32 or uint8, got {vol.dtype}")
+        if not (vol.is_cuda and vol.is_contiguous()):
+            raise ValueError(f"curr_obs_torch['{name}'] must be a contiguous CUDA tensor (channels-last (V,h,w,C))")
+        dt = _native.D3F_F32 if vol.dtype == torch.float32 else _native.D3F_U8
+        return (vol.data_ptr(), dt, int(vol.shape[1]), int(vol.shape[2]), int(vol.shape[3])), vol
+
+    def _flags(self, eval_dist=False):
+        f = _native.FLAG_EVAL_DIST if eval_dist else 0
+        if self.index_rounding == 'cuda':
+            f |= _native.FLAG_RECIP_NORM
+        elif self.index_rounding != 'cpu':
+            raise ValueError("index_rounding must be 'cpu' or 'cuda'")
+        return f
+
+    def _run(self, pts, return_names, return_inter, eval_dist):
+        self._check_pts(pts)
+        names = list(return_names)
+        V, H, W, pose_p, K_p, depth_p = self._obs_ptrs()
+        keys, keep = [], []
+        for k in ([] if eval_dist else names):
+            kt, vol = self._key_tuple(k, V)
+            keys.append(kt)
+            keep.append(vol)
+        n = int(pts.shape[0])
+        if not pts.is_cuda:
+            return self._run_host(pts, names, keys, V, H, W, pose_p, K_p, depth_p, eval_dist)
+        dev = self.curr_obs_torch['depth'].device
+        if pts.device != dev:
+            raise ValueError(f'pts is on {pts.device} but the observation is on {dev}')
+        pts = pts.contiguous()
+        with torch.cuda.device(dev):
+            dist = torch.empty(n, dtype=torch.float32, device=dev)
+            valid = torch.empty(n, dtype=torch.bool, device=dev)
+            outs = [torch.empty((n, kt[4]), dtype=torch.float32, device=dev) for kt in keys]
+            inters = [torch.empty((V, n, kt[4]), dtype=torch.float32, device=dev) for kt in keys] if return_inter else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _native.eval_device(V, H, W, pose_p, K_p, depth_p, pts.data_ptr(), n, keys,
+                                dist.data_ptr(), valid.data_ptr(), [o.data_ptr() for o in outs],
+                                [t.data_ptr() for t in inters] if inters is not None else None,
+                                self._flags(eval_dist), float(self.mu), stream)
+        res = {'dist': dist, 'valid_mask': valid}
+        for i, k in enumerate([] if eval_dist else names):
+            res[k] = outs[i]
+            if return_inter:
+                res[k + '_inter'] = inters[i]
+        return res
+
+    def _run_host(self, pts, names, keys, V, H, W, pose_p, K_p, depth_p, eval_dist, out=None):
+        """CPU points in, CPU results out: one d3f_eval_host call (slab-pipelined H2D/kernel/D2H)."""
+        n = int(pts.shape[0])
+        pts = pts.contiguous()
+        dev = self.curr_obs_torch['depth'].device
+        pin = True
+
+        def buf(name, shape, dtype):
+            if out is not None and name in out:
+                t = out[name]
+                if tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_contiguous() or t.is_cuda:
+                    raise ValueError(f"out['{name}'] must be a contiguous CPU {dtype} tensor of shape {tuple(shape)}")
+                return t
+            return torch.empty(shape, dtype=dtype, pin_memory=pin)
+
+        dist = buf('dist', (n,), torch.float32)
+        valid = buf('valid_mask', (n,), torch.bool)
+        outs = [buf(k, (n, kt[4]), torch.float32) for k, kt in zip(names, keys)]
+        with torch.cuda.device(dev):
+            _native.eval_host(V, H, W, pose_p, K_p, depth_p, pts.data_ptr(), n, keys,
+                              dist.data_ptr(), valid.data_ptr(), [o.data_ptr() for o in outs],
+                              self._flags(eval_dist), float(self.mu))
+        res = {'dist': dist, 'valid_mask': valid}
+        for k, o in zip(names, outs):
+            res[k] = o
+        return res
+
+    def eval(self, pts, return_names=['dino_feats', 'mask'], return_inter=False):
+        """(N,3) world points -> {'dist' (N,), 'valid_mask' (N,) bool, '<k>' (N,C_k) for k in return_names
+        [, '<k>_inter' (V,N,C_k)]}.  Reference fusion.py:305-394.  CPU `pts` give CPU results through the
+        host-buffer entry point (return_inter is device-only)."""
+        if isinstance(pts, torch.Tensor) and not pts.is_cuda and return_inter:
+            raise ValueError('return_inter needs device points')
+        return self._run(pts, return_names, return_inter, eval_dist=False)
+
+    def eval_dist(self, pts):
+        """Unclamped signed distance: {'dist', 'valid_mask'}.  Reference fusion.py:396-436."""
+        return self._run(pts, [], False, eval_dist=True)
+
+    def batch_eval(self, pts, return_names=['dino_feats', 'mask']):
+        """Reference fusion.py:526-545 chunks by 60 000 points to bound its (V,n,C) temporaries; this
+        path has none, so the whole batch is one launch and the result is the same dict."""
+        return self.eval(pts, return_names=return_names)
+
+    def eval_host(self, pts, return_names: Iterable[str] = (), out: Optional[dict] = None):
+        """Host-buffer evaluation with optional preallocated (ideally pinned) outputs."""
+        self._check_pts(pts)
+        if pts.is_cuda:
+            raise ValueError('eval_host takes CPU points')
+        names = list(return_names)
+        V, H, W, pose_p, K_p, depth_p = self._obs_ptrs()
+        keys = [self._key_tuple(k, V)[0] for k in names]
+        return self._run_host(pts, names, keys, V, H, W, pose_p, K_p, depth_p, False, out=out)
+
+    # ------------------------------------------------------------------ descriptors -> PCA
+    def pca_project(self, feats, mean, components):
+        """(feats - mean) @ components.T on the device: sklearn PCA.transform as the reference applies it
+        to descriptors on the host (fusion.py:1386-1392).  feats (N,C), mean (C,), components (k,C)."""
+        dev = feats.device
+        mean = _as_device(mean, dev, torch.float32).contiguous()
+        components = _as_device(components, dev, torch.float32).contiguous()
+        feats = feats.contiguous()
+        n, c = feats.shape
+        k = components.shape[0]
+        y = torch.empty((n, k), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _native.pca_project(feats.data_ptr(), n, c, mean.data_ptr(), components.data_ptr(), k, y.data_ptr(),
+                                torch.cuda.current_stream(dev).cuda_stream)
+        return y
+
+
+def project_points_coords(pts, Rt, K):
+    """Reference fusion.py:32-55, kept for callers that import it: (pts_2d (V,N,2), valid (V,N), depth (V,N,1)).
+    Not on the hot path (eval projects inside its kernel); computed with the same float32 sequence in torch."""
+    V, N = Rt.shape[0], pts.shape[0]
+    KRt = torch.zeros((V, 3, 4), dtype=pts.dtype, device=pts.device)
+    for k in range(3):
+        KRt = KRt + K[:, :, k:k + 1] * Rt[:, k:k + 1, :]
+    hp = torch.cat([pts, torch.ones((N, 1), dtype=pts.dtype, device=pts.device)], 1)
+    cam = torch.zeros((V, N, 3), dtype=pts.dtype, device=pts.device)
+    for k in range(4):
+        cam = cam + KRt[:, None, :, k] * hp[None, :, k:k + 1]
+    depth = cam[:, :, 2:].clone()
+    bad = depth.abs() < 1e-4
+    depth[bad] = 1e-3
+    return cam[:, :, :2] / depth, ~bad[..., 0], depth
+
+
+def interpolate_feats(feats, points, h=None, w=None, padding_mode='zeros', align_corners=False, inter_mode='bilinear'):
+    """Reference fusion.py:57-77, kept for callers that import it: feats (b,f,h,w), points (b,n,2) in pixels
+    of an (h,w) image -> (b,n,f).  Not on the hot path (eval samples inside its kernel)."""
+    import torch.nn.functional as F
+    b, _, ch, cw = feats.shape
+    if h is None and w is None:
+        h, w = ch, cw
+    gx = points[:, :, 0] / (w - 1) * 2 - 1
+    gy = points[:, :, 1] / (h - 1) * 2 - 1
+    grid = torch.stack([gx, gy], -1).unsqueeze(1)
+    out = F.grid_sample(feats, grid, mode=inter_mode, padding_mode=padding_mode, align_corners=align_corners)
+    return out.squeeze(2).permute(0, 2, 1)

@@ -1,0 +1,59 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports exactly what include/d3f.h declares;
+host-side argument checking works without a GPU (no compute calls here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from d3fields_b200 import _native, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'd3f.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(d3f_[a-z_0-9]+)\s*\(', src)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == sorted(_native.SYMBOLS)
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    for s in _declared_symbols():
+        assert hasattr(lib, s), f'{s} declared in include/d3f.h but not exported by libd3f.so'
+    out = subprocess.run(['nm', '-D', '--defined-only', path], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r' T (d3f_[a-z_0-9]+)', out)))
+    assert exported == _declared_symbols()
+
+
+def test_library_is_sm100a_only_and_has_no_torch_dependency():
+    path = build.build()
+    out = subprocess.run(['cuobjdump', '--list-elf', path], capture_output=True, text=True).stdout
+    archs = set(re.findall(r'sm_(\d+a?)', out))
+    assert archs == {'100a'}, archs
+    ldd = subprocess.run(['ldd', path], capture_output=True, text=True).stdout
+    assert 'torch' not in ldd and 'c10' not in ldd
+
+
+def test_abi_version_and_argument_validation_without_gpu():
+    lib = _native.load()
+    assert lib.d3f_abi_version() == _native.ABI_VERSION
+    obs = _native.D3FObs(0, 480, 640, 1, 1, 1)        # V = 0 is rejected before any CUDA call
+    rc = lib.d3f_eval(ctypes.byref(obs), 1, 10, None, 0, 1, 1, None, None, 0, 0.02, None)
+    assert rc == -1 and b'V=0' in lib.d3f_last_error()
+    obs = _native.D3FObs(4, 480, 640, 1, 1, 1)
+    rc = lib.d3f_eval(ctypes.byref(obs), 1, 10, None, 0, 1, 1, None, None, 0, -1.0, None)
+    assert rc == -1 and b'mu' in lib.d3f_last_error()
+    rc = lib.d3f_eval(ctypes.byref(obs), 1, 10, None, 3, 1, 1, None, None, 0, 0.02, None)
+    assert rc == -1 and b'keys' in lib.d3f_last_error()
+    rc = lib.d3f_eval(ctypes.byref(obs), 1, 10, None, 0, 1, 1, None, None, 64, 0.02, None)
+    assert rc == -1 and b'flag' in lib.d3f_last_error()
+    with pytest.raises(_native.D3FError):
+        _native.eval_device(99, 4, 4, 1, 1, 1, 1, 1, [], 1, 1, [], None, 0, 0.02, 0)

@@ -43,3 +43,19 @@ def test_uint8_mask_is_read_as_its_float_value():
     a = O.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, m8, ['mask'], mu=g.mu)
     b = O.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, ['mask'], mu=g.mu)
     assert np.array_equal(a['mask'], b['mask'])
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_torch_port_matches_reference_golden(name):
+    """oracle/torch_port.py (the CPU-baseline stand-in for the reference) gives the reference's results."""
+    import torch
+    from oracle import torch_port as TP
+    g = Golden(name)
+    sc = g.scene
+    obs = TP.obs_from_scene(sc)
+    pts = torch.from_numpy(g.pts)
+    out = TP.batch_eval(obs, sc.H, sc.W, pts, g.names, mu=g.mu)
+    g.check_exact('dist', out['dist'].numpy())
+    g.check_exact('valid_mask', out['valid_mask'].numpy())
+    for k in g.names:
+        g.check_close(k, out[k].numpy())

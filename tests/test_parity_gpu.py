@@ -1,0 +1,270 @@
+"""GPU: the CUDA path, called through the public Fusion API -> ctypes -> C ABI, against
+  (1) the golden vectors the unmodified reference produced (tests/golden/, oracle/gen_golden.py),
+  (2) the CPU oracle (oracle/field_oracle.py) on seeded inputs at sizes the oracle finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full size (1M points, V=4, C=1024).
+
+Bars: dist and valid_mask bit-exact (they are decided by the integer pixel index and an ordered float32
+sum); descriptors |a-b| <= 1e-4*|b| + 2e-6*max|b| (north_star: "fp32 descriptors within 1e-4 relative").
+"""
+import numpy as np
+import pytest
+import torch
+
+from d3fields_b200 import _native, scene as S
+from golden_util import CASES, Golden
+from oracle import field_oracle as O
+from util import assert_bits_equal, assert_close_field, make_fusion
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _np(d):
+    return {k: v.detach().cpu().numpy() for k, v in d.items()}
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _native_library_is_the_one_running():
+    lib = _native.load()
+    assert lib.d3f_abi_version() == _native.ABI_VERSION
+    before = _native.launch_count()
+    yield
+    assert _native.launch_count() > before, 'no kernel of libd3f.so was launched by the GPU tests'
+
+
+# ---------------------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize('name', CASES)
+def test_matches_reference_golden(name):
+    g = Golden(name)
+    f = make_fusion(g.scene, DEV, mu=g.mu)
+    pts = torch.from_numpy(g.pts).to(DEV)
+    if g.meta['batch']:
+        out = _np(f.batch_eval(pts, return_names=g.names))
+    else:
+        out = _np(f.eval(pts, return_names=g.names, return_inter=True))
+    g.check_exact('dist', out['dist'])
+    g.check_exact('valid_mask', out['valid_mask'])
+    for k in g.names:
+        g.check_close(k, out[k])
+        if not g.meta['batch']:
+            g.check_close(k + '_inter', out[k + '_inter'])
+    od = _np(f.eval_dist(pts))
+    g.check_exact('evaldist.dist', od['dist'])
+    g.check_exact('evaldist.valid_mask', od['valid_mask'])
+
+
+# ---------------------------------------------------------------------------- oracle, seeded cases
+ORACLE_CASES = [
+    # V, H, W, feat(h,w,C), num_inst, n_grid, n_scatter, seed
+    (1, 60, 80, (6, 8, 4), 2, (9, 9, 9), 500, 10),
+    (2, 240, 320, (24, 32, 64), 8, (20, 20, 10), 3000, 11),
+    (4, 480, 640, (48, 64, 256), 8, (24, 24, 24), 4000, 12),
+    (4, 480, 640, (48, 64, 1024), 0, (16, 16, 16), 2000, 13),        # cfg2a channels
+    (6, 120, 160, (12, 16, 12), 5, (11, 13, 7), 1234, 14),
+    (3, 97, 131, (97, 131, 7), 3, (10, 10, 10), 777, 15),            # full-resolution map, odd C
+    (16, 48, 64, (5, 7, 3), 0, (8, 8, 8), 100, 16),                  # D3F_MAX_VIEWS
+]
+
+
+@pytest.mark.parametrize('case', ORACLE_CASES, ids=[f'V{c[0]}_C{c[3][2]}_{c[1]}x{c[2]}' for c in ORACLE_CASES])
+@pytest.mark.parametrize('mask_u8', [False, True])
+def test_matches_oracle(case, mask_u8):
+    V, H, W, feat, num_inst, grid, n_sc, seed = case
+    if mask_u8 and num_inst == 0:
+        pytest.skip('no mask in this case')
+    sc = S.make_scene(V, H, W, seed=seed, feat=feat, num_inst=num_inst, color=True)
+    pts = np.concatenate([S.grid_points(*grid), S.scattered_points(n_sc, seed), S.adversarial_points(sc, seed, 8)])
+    names = ['dino_feats', 'color_tensor'] + (['mask'] if num_inst else [])
+    f = make_fusion(sc, DEV, mask_u8=mask_u8)
+    got = _np(f.eval(torch.from_numpy(pts).to(DEV), return_names=names, return_inter=True))
+    ref = O.field_eval(pts, sc.pose, sc.K, sc.depth, H, W, sc.maps, names, return_inter=True)
+    assert got['valid_mask'].dtype == np.bool_ and got['dist'].dtype == np.float32
+    assert_bits_equal(got['valid_mask'], ref['valid_mask'], 'valid_mask')
+    assert_bits_equal(got['dist'], ref['dist'], 'dist')
+    assert 0.05 < ref['valid_mask'].mean() < 0.95          # the case exercises both outcomes
+    for k in names:
+        assert_close_field(got[k], ref[k], what=k)
+        assert_close_field(got[k + '_inter'], ref[k + '_inter'], what=k + '_inter')
+        # points no view sees: descriptors exactly 0, dist exactly 1e3 (reference fusion.py:367, :386)
+        none = ~ref['valid_mask']
+        assert (got[k][none] == 0).all()
+    assert (got['dist'][~ref['valid_mask']] == np.float32(1e3)).all()
+    gd = _np(f.eval_dist(torch.from_numpy(pts).to(DEV)))
+    rd = O.field_eval(pts, sc.pose, sc.K, sc.depth, H, W, eval_dist=True)
+    assert_bits_equal(gd['dist'], rd['dist'], 'eval_dist.dist')
+    assert_bits_equal(gd['valid_mask'], rd['valid_mask'], 'eval_dist.valid_mask')
+
+
+@pytest.mark.parametrize('n', [0, 1, 2, 31, 63, 64, 65, 127, 129, 1000, 4097])
+def test_ragged_sizes(n):
+    sc = S.make_scene(4, 120, 160, seed=21, feat=(12, 16, 128), num_inst=4)
+    pts = S.scattered_points(max(n, 1), 21, sigma=0.15)[:n]
+    f = make_fusion(sc, DEV)
+    got = _np(f.eval(torch.from_numpy(pts).to(DEV).reshape(n, 3), return_names=['dino_feats', 'mask']))
+    ref = O.field_eval(pts.reshape(n, 3), sc.pose, sc.K, sc.depth, 120, 160, sc.maps, ['dino_feats', 'mask'])
+    assert got['dist'].shape == (n,) and got['dino_feats'].shape == (n, 128) and got['mask'].shape == (n, 4)
+    assert_bits_equal(got['dist'], ref['dist'], 'dist')
+    assert_bits_equal(got['valid_mask'], ref['valid_mask'], 'valid_mask')
+    assert_close_field(got['dino_feats'], ref['dino_feats'], what='dino_feats')
+    assert_close_field(got['mask'], ref['mask'], what='mask')
+
+
+def test_dist_only_and_default_names_keyerror():
+    sc = S.make_scene(4, 120, 160, seed=22, feat=(12, 16, 8))
+    pts = S.grid_points(20, 20, 20)
+    f = make_fusion(sc, DEV)
+    got = _np(f.batch_eval(torch.from_numpy(pts).to(DEV), return_names=[]))
+    ref = O.field_eval(pts, sc.pose, sc.K, sc.depth, 120, 160)
+    assert set(got) == {'dist', 'valid_mask'}
+    assert_bits_equal(got['dist'], ref['dist'])
+    assert_bits_equal(got['valid_mask'], ref['valid_mask'])
+    with pytest.raises(KeyError):              # default return_names asks for 'mask' (reference fusion.py:305)
+        f.eval(torch.from_numpy(pts).to(DEV))
+
+
+def test_custom_mu():
+    sc = S.make_scene(3, 120, 160, seed=23, feat=(12, 16, 16))
+    pts = S.grid_points(16, 16, 16)
+    for mu in (0.005, 0.02, 0.1):
+        f = make_fusion(sc, DEV, mu=mu)
+        got = _np(f.eval(torch.from_numpy(pts).to(DEV), return_names=['dino_feats']))
+        ref = O.field_eval(pts, sc.pose, sc.K, sc.depth, 120, 160, sc.maps, ['dino_feats'], mu=mu)
+        assert_bits_equal(got['dist'], ref['dist'], f'dist mu={mu}')
+        assert_bits_equal(got['valid_mask'], ref['valid_mask'])
+        assert_close_field(got['dino_feats'], ref['dino_feats'], what=f'feats mu={mu}')
+
+
+def test_host_buffer_entry_point_equals_device_path():
+    sc = S.make_scene(4, 240, 320, seed=24, feat=(24, 32, 256), num_inst=8)
+    pts = np.concatenate([S.grid_points(40, 40, 40), S.scattered_points(7001, 24)])
+    f = make_fusion(sc, DEV, mask_u8=True)
+    dev = _np(f.eval(torch.from_numpy(pts).to(DEV), return_names=['dino_feats', 'mask']))
+    host = f.eval(torch.from_numpy(pts), return_names=['dino_feats', 'mask'])
+    assert all(not v.is_cuda for v in host.values())
+    for k in dev:
+        assert_bits_equal(host[k].numpy(), dev[k], k)
+    out = {'dino_feats': torch.empty((len(pts), 256), dtype=torch.float32).pin_memory()}
+    host2 = f.eval_host(torch.from_numpy(pts).pin_memory(), ['dino_feats'], out=out)
+    assert host2['dino_feats'].data_ptr() == out['dino_feats'].data_ptr()
+    assert_bits_equal(host2['dino_feats'].numpy(), dev['dino_feats'])
+    assert_bits_equal(f.eval_host(torch.from_numpy(pts))['dist'].numpy(), dev['dist'])
+
+
+def test_non_default_stream_and_noncontiguous_points():
+    sc = S.make_scene(2, 120, 160, seed=25, feat=(12, 16, 32))
+    pts = S.scattered_points(5000, 25)
+    f = make_fusion(sc, DEV)
+    base = _np(f.eval(torch.from_numpy(pts).to(DEV), return_names=['dino_feats']))
+    wide = torch.zeros((5000, 6), device=DEV)
+    wide[:, ::2] = torch.from_numpy(pts).to(DEV)
+    s = torch.cuda.Stream(DEV)
+    s.wait_stream(torch.cuda.current_stream(DEV))
+    with torch.cuda.stream(s):
+        got = f.eval(wide[:, ::2], return_names=['dino_feats'])
+    s.synchronize()
+    for k in base:
+        assert_bits_equal(got[k].cpu().numpy(), base[k], k)
+
+
+def test_torch_cuda_rounding_flag_changes_only_boundary_pixels():
+    """index_rounding='cuda' replays torch's CUDA kernels' rounding of the pixel normalisation; it may flip
+    a handful of nearest/floor decisions that sit within float rounding of a pixel border, nothing else."""
+    sc = S.make_scene(4, 480, 640, seed=26, feat=(48, 64, 16))
+    pts = S.grid_points(40, 40, 40)
+    f = make_fusion(sc, DEV)
+    a = _np(f.eval(torch.from_numpy(pts).to(DEV), return_names=['dino_feats']))
+    f.index_rounding = 'cuda'
+    b = _np(f.eval(torch.from_numpy(pts).to(DEV), return_names=['dino_feats']))
+    assert (a['valid_mask'] != b['valid_mask']).mean() < 1e-3
+    same = a['dist'] == b['dist']
+    assert same.mean() > 0.99
+
+
+# ---------------------------------------------------------------------------- full size: properties
+@pytest.fixture(scope='module')
+def cfg2a():
+    c = S.CONFIGS['cfg2a']
+    sc = S.make_scene(c['V'], c['H'], c['W'], seed=0, feat=c['feat'])
+    pts = S.config_points('cfg2a')
+    f = make_fusion(sc, DEV)
+    p = torch.from_numpy(pts).to(DEV)
+    out = f.batch_eval(p, return_names=['dino_feats'])
+    torch.cuda.synchronize()
+    return sc, pts, f, p, out
+
+
+def test_full_size_sampled_rows_match_oracle(cfg2a):
+    sc, pts, f, p, out = cfg2a
+    rs = np.random.RandomState(5)
+    rows = np.sort(rs.choice(len(pts), 3000, replace=False))
+    ref = O.field_eval(pts[rows], sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, ['dino_feats'])
+    idx = torch.from_numpy(rows).to(DEV)
+    assert_bits_equal(out['dist'][idx].cpu().numpy(), ref['dist'], 'dist')
+    assert_bits_equal(out['valid_mask'][idx].cpu().numpy(), ref['valid_mask'], 'valid_mask')
+    assert_close_field(out['dino_feats'][idx].cpu().numpy(), ref['dino_feats'], what='dino_feats')
+    assert 0.2 < ref['valid_mask'].mean() < 0.9
+
+
+def test_full_size_dist_valid_match_oracle_everywhere(cfg2a):
+    sc, pts, f, p, out = cfg2a
+    ref = O.field_eval(pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, chunk=1 << 17)
+    assert_bits_equal(out['dist'].cpu().numpy(), ref['dist'], 'dist (1M)')
+    assert_bits_equal(out['valid_mask'].cpu().numpy(), ref['valid_mask'], 'valid_mask (1M)')
+
+
+def test_full_size_permutation_and_slicing_invariance(cfg2a):
+    """Every point is independent (reference fusion.py:305-394 has no cross-point term): evaluating a
+    permutation or a slice must give bit-identical rows, whatever tile/cache state they land in."""
+    sc, pts, f, p, out = cfg2a
+    g = torch.Generator(device='cpu').manual_seed(3)
+    perm = torch.randperm(len(pts), generator=g)[:200_000].to(DEV)
+    o2 = f.eval(p[perm].contiguous(), return_names=['dino_feats'])
+    assert torch.equal(o2['dist'], out['dist'][perm])
+    assert torch.equal(o2['valid_mask'], out['valid_mask'][perm])
+    assert torch.equal(o2['dino_feats'], out['dino_feats'][perm])
+    a, b = 123_457, 323_456
+    o3 = f.eval(p[a:b], return_names=['dino_feats'])
+    assert torch.equal(o3['dino_feats'], out['dino_feats'][a:b])
+    assert torch.equal(o3['dist'], out['dist'][a:b])
+
+
+def test_full_size_linearity_in_the_feature_volume(cfg2a):
+    """The field is linear in the sampled map: F(2*A) == 2*F(A) exactly (power-of-two scaling is exact in
+    float32), and F(const) has every valid row equal to const * sum of its weights."""
+    sc, pts, f, p, out = cfg2a
+    vol = f.curr_obs_torch['dino_feats']
+    f.curr_obs_torch['dino_feats'] = (vol * 2).contiguous()
+    o2 = f.eval(p[:300_000], return_names=['dino_feats'])
+    assert torch.equal(o2['dino_feats'], out['dino_feats'][:300_000] * 2)
+    f.curr_obs_torch['dino_feats'] = torch.ones_like(vol)
+    o1 = f.eval(p[:300_000], return_names=['dino_feats'])['dino_feats']
+    spread = (o1.max(1).values - o1.min(1).values)
+    assert float(spread.max()) == 0.0                      # all channels of a row see the same weights
+    assert float(o1.max()) <= 1.0 + 1e-5 and float(o1.min()) >= 0.0
+    f.curr_obs_torch['dino_feats'] = vol
+
+
+# ---------------------------------------------------------------------------- neighbours of the path
+def test_pca_projection_matches_numpy():
+    rs = np.random.RandomState(0)
+    for n, c, k in ((1000, 1024, 3), (257, 64, 8), (33, 7, 2)):
+        x = rs.standard_normal((n, c)).astype(np.float32)
+        mean = rs.standard_normal(c).astype(np.float32)
+        comp = rs.standard_normal((k, c)).astype(np.float32)
+        f = make_fusion(S.make_scene(1, 8, 8, seed=0), DEV)
+        y = f.pca_project(torch.from_numpy(x).to(DEV), mean, comp).cpu().numpy()
+        ref = (x.astype(np.float64) - mean) @ comp.T.astype(np.float64)
+        assert np.abs(y - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_device_grid_matches_create_init_grid():
+    from d3fields_b200 import create_init_grid
+    b = S.WORKSPACE
+    step = 0.01
+    ref, shape = create_init_grid(b, step)
+    nx, ny, nz = shape
+    pts = torch.empty((nx * ny * nz, 3), dtype=torch.float32, device=DEV)
+    _native.create_grid(b['x_lower'], b['y_lower'], b['z_lower'], step, nx, ny, nz, pts.data_ptr(),
+                        torch.cuda.current_stream().cuda_stream)
+    d = (pts.cpu() - ref).abs().max().item()
+    assert d <= 6e-8, d            # torch.arange's vectorised path may differ from the scalar formula by 1 ulp
