@@ -104,6 +104,19 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
     const int64_t tiles = (n + d3f::GEN_TILE_PTS - 1) / d3f::GEN_TILE_PTS;
     if (tiles > 0x7fffffffll) return fail(D3F_EINVAL, "n=%lld too large for one launch", (long long)n);
     const size_t smem = d3f::generic_smem_bytes(obs->V);
+    if (smem > 48 * 1024) {     // V > 15: opt in to more than the default 48 KB of dynamic shared memory
+        static std::once_flag once;
+        static cudaError_t attr_err = cudaSuccess;
+        std::call_once(once, [] {
+            const int big = (int)d3f::generic_smem_bytes(D3F_MAX_VIEWS);
+            cudaError_t e;
+            if ((e = cudaFuncSetAttribute(d3f::field_generic_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))) attr_err = e;
+            if ((e = cudaFuncSetAttribute(d3f::field_generic_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))) attr_err = e;
+            if ((e = cudaFuncSetAttribute(d3f::field_generic_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))) attr_err = e;
+            if ((e = cudaFuncSetAttribute(d3f::field_generic_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))) attr_err = e;
+        });
+        if (attr_err != cudaSuccess) return fail(D3F_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
+    }
     dim3 grid((unsigned)tiles), block(d3f::GEN_THREADS);
     if (any_inter) {
         if (recip) d3f::field_generic_kernel<true, true><<<grid, block, smem, st>>>(ep, ks);
