@@ -11,6 +11,7 @@
 #include "../../include/d3f.h"
 #include "d3f_common.cuh"
 #include "d3f_generic.cuh"
+#include "d3f_tile.cuh"
 #include "d3f_aux.cuh"
 
 namespace {
@@ -101,6 +102,21 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
         }
         g_variant[k] = "generic";
     }
+    // production path: 128-point tiles, register-cached corner texels for wide float32 maps
+    bool tile_ok = obs->V <= d3f::TILE_V && !any_inter;
+    for (int k = 0; k < ks.n_keys; ++k) tile_ok &= ((int64_t)keys[k].h * keys[k].w < (1ll << 29));
+    if (tile_ok) {
+        const int64_t tiles = (n + d3f::TILE_PTS - 1) / d3f::TILE_PTS;
+        if (tiles > 0x7fffffffll) return fail(D3F_EINVAL, "n=%lld too large for one launch", (long long)n);
+        for (int k = 0; k < ks.n_keys; ++k)
+            g_variant[k] = d3f::key_is_wide(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w) ? "tile/wide" : "tile/narrow";
+        dim3 grid((unsigned)tiles), block(d3f::TILE_THREADS);
+        if (recip) d3f::field_tile_kernel<true><<<grid, block, 0, st>>>(ep, ks);
+        else       d3f::field_tile_kernel<false><<<grid, block, 0, st>>>(ep, ks);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        D3F_CUDA(cudaGetLastError());
+        return D3F_OK;
+    }
     const int64_t tiles = (n + d3f::GEN_TILE_PTS - 1) / d3f::GEN_TILE_PTS;
     if (tiles > 0x7fffffffll) return fail(D3F_EINVAL, "n=%lld too large for one launch", (long long)n);
     const size_t smem = d3f::generic_smem_bytes(obs->V);
@@ -176,7 +192,7 @@ int d3f_eval_host(const D3FObs* obs, const float* pts_host, int64_t n, const D3F
     int64_t slab = (int64_t)((32ull << 20) / per_pt);
     if (slab < 4096) slab = 4096;
     if (slab > (1 << 20)) slab = 1 << 20;
-    slab = (slab / d3f::GEN_TILE_PTS) * d3f::GEN_TILE_PTS;
+    slab = (slab / d3f::TILE_PTS) * d3f::TILE_PTS;
     if (slab > n) slab = n;
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t need = up((size_t)slab * 12) + up((size_t)slab * 4) + up((size_t)slab) +

@@ -1,0 +1,227 @@
+// d3f_tile.cuh — the production field-query kernel (V <= 4, no per-view outputs).
+//
+// One CTA (256 threads) evaluates a tile of 128 consecutive query points:
+//
+//   phase 0/1/1r  as in d3f_generic.cuh: H = [K@Rt;0001], one thread per (point, view) for
+//                 projection / nearest depth / visibility / distance weight, then one thread per
+//                 point reduces the views in order -> dist, valid_mask, per-view factor
+//   per key       one thread per (point, view) turns the pixel coordinate into a bilinear footprint
+//                 on that key's map: four corner weights already multiplied by the view factor
+//                 weight/(count+1e-6), and one packed code (north-west texel offset, east/south
+//                 step bits; -1 when the view does not see the point)
+//   wide maps     (float32, C % 128 == 0, e.g. the 1024-channel DINOv2 volume): a warp owns a
+//                 128-channel slice (one float4 per lane) and marches over the tile's points in
+//                 order.  The four corner texels of each view stay in registers and are reloaded
+//                 only when the packed code changes — neighbouring grid points project into the
+//                 same texel cell most of the time, so the 16 KB-per-point gather of the reference
+//                 (4 views x 4 corners x C floats) collapses to a reload every few points, served
+//                 by L1/L2 (the whole volume is L2-resident).  Per visible view the inner loop is
+//                 one 128-bit shared-memory read of the folded weights and 16 FFMA per lane; the
+//                 output row is written once with 128-bit streaming stores (st.global.cs), 512
+//                 contiguous bytes per warp, so the 4 KB/point output stream never evicts the
+//                 feature volume from L2.
+//   narrow maps   (instance masks, colours; u8 or f32, any C): threads sweep (point, channel-group).
+//
+// HBM traffic is the algorithmic minimum: points and depth pixels in, each output byte out once; the
+// feature volume is read from HBM once and then lives in L2.
+#pragma once
+#include "d3f_common.cuh"
+#include "d3f_generic.cuh"
+
+namespace d3f {
+
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_PTS = 128;
+constexpr int TILE_V = 4;             // views supported by this kernel (slots are padded to 4)
+
+struct TileSmem {
+    float H[TILE_V * 12];
+    float px[TILE_PTS * TILE_V];
+    float py[TILE_PTS * TILE_V];
+    float d[TILE_PTS * TILE_V];
+    float fac[TILE_PTS * TILE_V];
+    int vis[TILE_PTS * TILE_V];
+    float4 w4[TILE_PTS * TILE_V];     // folded corner weights per (point, view)
+    int4 code[TILE_PTS];              // packed footprint codes of the 4 views of a point
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// One view's contribution to a lane's 4 channels, with the corner cache.
+#define D3F_WIDE_VIEW(v, cv)                                                                       \
+    if ((cv) >= 0) {                                                                               \
+        if ((cv) != cur[v]) {                                                                      \
+            const float* b_ = vb + (size_t)(v) * vstride + (size_t)((cv) >> 2) * (size_t)C;        \
+            const int dx_ = ((cv) & 1) ? C : 0;                                                    \
+            const int dy_ = ((cv) & 2) ? rowC : 0;                                                 \
+            cc[v][0] = ldg4(b_); cc[v][1] = ldg4(b_ + dx_);                                        \
+            cc[v][2] = ldg4(b_ + dy_); cc[v][3] = ldg4(b_ + dy_ + dx_);                            \
+            cur[v] = (cv);                                                                         \
+        }                                                                                          \
+        const float4 w_ = sm.w4[p * TILE_V + (v)];                                                 \
+        fma4(acc, w_.x, cc[v][0]); fma4(acc, w_.y, cc[v][1]);                                      \
+        fma4(acc, w_.z, cc[v][2]); fma4(acc, w_.w, cc[v][3]);                                      \
+    }
+
+__device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmem& sm) {
+    const int C = kp.C;
+    const int S = C >> 7;                                   // 128-channel slices
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = TILE_THREADS / 32;
+    int s0, sstep, p_begin, p_end;
+    if (S >= nwarps) {                                      // every warp walks the whole tile on its slices
+        s0 = warp; sstep = nwarps; p_begin = 0; p_end = npts;
+    } else {                                                // fewer slices than warps: split the tile into runs
+        const int R = nwarps / S;
+        const int r = warp / S;
+        if (r >= R) return;
+        const int run = (TILE_PTS + R - 1) / R;
+        s0 = warp - r * S; sstep = S;
+        p_begin = r * run; p_end = min(p_begin + run, npts);
+    }
+    const float* __restrict__ vol = static_cast<const float*>(kp.data);
+    const size_t vstride = (size_t)kp.h * kp.w * C;
+    const int rowC = kp.w * C;
+    for (int s = s0; s < S; s += sstep) {
+        const float* vb = vol + s * 128 + lane * 4;
+        float* o = kp.out + (size_t)(tile0 + p_begin) * C + s * 128 + lane * 4;
+        float4 cc[TILE_V][4];
+        int cur[TILE_V] = {-1, -1, -1, -1};
+        for (int p = p_begin; p < p_end; ++p, o += C) {
+            const int4 code = sm.code[p];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            D3F_WIDE_VIEW(0, code.x)
+            D3F_WIDE_VIEW(1, code.y)
+            D3F_WIDE_VIEW(2, code.z)
+            D3F_WIDE_VIEW(3, code.w)
+            __stcs(reinterpret_cast<float4*>(o), acc);
+        }
+    }
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmem& sm) {
+    const int C = kp.C;
+    const int G = C / VEC;
+    const T* __restrict__ vol = static_cast<const T*>(kp.data);
+    const size_t vstride = (size_t)kp.h * kp.w * C;
+    const int rowC = kp.w * C;
+    const int* codes = reinterpret_cast<const int*>(sm.code);
+    for (int item = threadIdx.x; item < npts * G; item += TILE_THREADS) {
+        const int p = item / G;
+        const int c = (item - p * G) * VEC;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int v = 0; v < TILE_V; ++v) {
+            const int cv = codes[p * TILE_V + v];
+            if (cv < 0) continue;
+            const T* b = vol + (size_t)v * vstride + (size_t)(cv >> 2) * (size_t)C + c;
+            const int dx = (cv & 1) ? C : 0, dy = (cv & 2) ? rowC : 0;
+            const float4 w = sm.w4[p * TILE_V + v];
+            if (VEC == 4) {
+                fma4(acc, w.x, Load4<T>::ld(b)); fma4(acc, w.y, Load4<T>::ld(b + dx));
+                fma4(acc, w.z, Load4<T>::ld(b + dy)); fma4(acc, w.w, Load4<T>::ld(b + dy + dx));
+            } else {
+                acc.x = fmaf(w.x, Load4<T>::ld1(b), acc.x); acc.x = fmaf(w.y, Load4<T>::ld1(b + dx), acc.x);
+                acc.x = fmaf(w.z, Load4<T>::ld1(b + dy), acc.x); acc.x = fmaf(w.w, Load4<T>::ld1(b + dy + dx), acc.x);
+            }
+        }
+        float* o = kp.out + (size_t)(tile0 + p) * C + c;
+        if (VEC == 4) __stcs(reinterpret_cast<float4*>(o), acc);
+        else          __stcs(o, acc.x);
+    }
+}
+
+// wide-path eligibility of one key (host and device agree through this one function)
+__host__ __device__ inline bool key_is_wide(int dtype, int C, int h, int w) {
+    return dtype == D3F_F32 && (C % 128) == 0 && (long long)h * w < (1ll << 29);
+}
+
+template <bool RECIP>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+field_tile_kernel(const EvalParams ep, const KeySet ks) {
+    __shared__ TileSmem sm;
+    const int V = ep.V;
+    const bool eval_dist = (ep.flags & D3F_FLAG_EVAL_DIST) != 0;
+    const int64_t tile0 = (int64_t)blockIdx.x * TILE_PTS;
+    const int npts = (int)min((int64_t)TILE_PTS, ep.n - tile0);
+
+    for (int r = threadIdx.x; r < V * 3; r += TILE_THREADS) {
+        const int v = r / 3, i = r - v * 3;
+        float row[4];
+        krt_row(ep.K + v * 9, ep.pose + v * 12, i, row);
+        sm.H[v * 12 + i * 4 + 0] = row[0]; sm.H[v * 12 + i * 4 + 1] = row[1];
+        sm.H[v * 12 + i * 4 + 2] = row[2]; sm.H[v * 12 + i * 4 + 3] = row[3];
+    }
+    __syncthreads();
+
+    // phase 1: view-major so a warp walks 32 consecutive points of one view
+    for (int item = threadIdx.x; item < TILE_PTS * V; item += TILE_THREADS) {
+        const int v = item / TILE_PTS, p = item - v * TILE_PTS;
+        if (p >= npts) continue;
+        const float* q = ep.pts + (size_t)(tile0 + p) * 3;
+        const float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+        float Hm[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) Hm[j] = sm.H[v * 12 + j];
+        ViewSample smp = view_sample<RECIP>(Hm, x, y, z, ep.depth + (size_t)v * ep.H * ep.W, ep.H, ep.W, ep.mu, eval_dist);
+        const int s = p * TILE_V + v;
+        sm.px[s] = smp.px; sm.py[s] = smp.py;
+        sm.d[s] = eval_dist ? smp.d : fminf(fmaxf(smp.d, -ep.mu), ep.mu);    // fusion.py:358
+        sm.fac[s] = smp.weight;
+        sm.vis[s] = smp.vis ? 1 : 0;
+    }
+    __syncthreads();
+
+    // phase 1r: views in order (fusion.py:364-370)
+    if (threadIdx.x < npts) {
+        const int p = threadIdx.x;
+        float acc = 0.f, cnt = 0.f;
+        for (int v = 0; v < V; ++v)
+            if (sm.vis[p * TILE_V + v]) { acc = __fadd_rn(acc, sm.d[p * TILE_V + v]); cnt = __fadd_rn(cnt, 1.f); }
+        const float denom = __fadd_rn(cnt, 1e-6f);
+        float dist = __fdiv_rn(acc, denom);
+        if (!eval_dist && cnt == 0.f) dist = 1e3f;                           // fusion.py:367
+        ep.dist[tile0 + p] = dist;
+        ep.valid[tile0 + p] = cnt != 0.f ? 1 : 0;
+        const float inv = __fdiv_rn(1.f, denom);
+        for (int v = 0; v < V; ++v) {
+            const int s = p * TILE_V + v;
+            sm.fac[s] = sm.vis[s] ? __fmul_rn(sm.fac[s], inv) : 0.f;          // weight/(count+1e-6), fusion.py:385
+        }
+    }
+    if (eval_dist || ks.n_keys == 0) return;
+    __syncthreads();
+
+    int* codes = reinterpret_cast<int*>(sm.code);
+    for (int k = 0; k < ks.n_keys; ++k) {
+        const KeyParams& kp = ks.k[k];
+        for (int s = threadIdx.x; s < TILE_PTS * TILE_V; s += TILE_THREADS) {
+            const int p = s >> 2, v = s & 3;
+            int code = -1;
+            if (p < npts && v < V && sm.vis[s]) {
+                const Footprint f = footprint<RECIP>(sm.px[s], sm.py[s], ep.H, ep.W, kp.h, kp.w);
+                const float fac = sm.fac[s];
+                sm.w4[s] = make_float4(f.w[0] * fac, f.w[1] * fac, f.w[2] * fac, f.w[3] * fac);
+                code = (f.off << 2) | (f.dx ? 1 : 0) | (f.dy ? 2 : 0);
+            }
+            codes[s] = code;
+        }
+        __syncthreads();
+        if (key_is_wide(ks.dtype[k], kp.C, kp.h, kp.w)) {
+            wide_accumulate(kp, tile0, npts, sm);
+        } else {
+            const bool vec4 = (kp.C % 4 == 0);
+            if (ks.dtype[k] == D3F_F32) {
+                if (vec4) narrow_accumulate<float, 4>(kp, tile0, npts, sm);
+                else      narrow_accumulate<float, 1>(kp, tile0, npts, sm);
+            } else {
+                if (vec4) narrow_accumulate<uint8_t, 4>(kp, tile0, npts, sm);
+                else      narrow_accumulate<uint8_t, 1>(kp, tile0, npts, sm);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace d3f

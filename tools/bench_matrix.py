@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Secondary measurements for DESIGN.md (not the driver's bench contract): every BASELINE.json config that
+fits one GPU, timed with CUDA events through the public Fusion API, plus the reference's operator sequence
+run on the same GPU by torch (oracle/torch_port.py on device='cuda') as the "torch-GPU" column.
+
+    python tools/bench_matrix.py [--out gpurun_out/matrix.jsonl] [--only name,...]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from d3fields_b200 import Fusion, _native, scene as S  # noqa: E402
+
+DEV = 'cuda:0'
+
+
+def timed(fn, warm=3, reps=10, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(min(ts))
+
+
+def alg_bytes(n, V, H, W, keys):
+    b = 12 * n + min(V * H * W * 4, 4 * n * V) + n * 5
+    for (h, w, C, s) in keys:
+        b += min(V * h * w * C * s, 4 * n * V * C * s) + n * 4 * C
+    return b
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'matrix.jsonl'))
+    ap.add_argument('--only', default='')
+    args = ap.parse_args()
+    only = set(x for x in args.only.split(',') if x)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    V, H, W = 4, 480, 640
+    sc = S.make_scene(V, H, W, seed=0, feat=(48, 64, 1024), num_inst=8, color=True)
+    f = Fusion(num_cam=V, device=DEV)
+    f.update({'depth': sc.depth, 'pose': sc.pose, 'K': sc.K, 'dino_feats': sc.maps['dino_feats']})
+    f.curr_obs_torch['mask'] = torch.from_numpy(sc.maps['mask']).to(DEV)
+    f.curr_obs_torch['mask_u8'] = torch.from_numpy(sc.maps['mask']).to(DEV).to(torch.uint8)
+    f.curr_obs_torch['color_tensor'] = torch.from_numpy(sc.maps['color_tensor']).to(DEV)
+    grid1m = torch.from_numpy(S.config_points('cfg2a')).to(DEV)
+    scat1m = torch.from_numpy(S.scattered_points(1_000_000, 0)).to(DEV)
+    scat256k = scat1m[:262144].contiguous()
+    grid16m = torch.from_numpy(S.grid_points(400, 200, 200)).to(DEV)
+    results = []
+
+    def rec(name, n, ms, ms_min, keys, note=''):
+        B = alg_bytes(n, V, H, W, keys)
+        r = dict(name=name, n=n, ms=ms, ms_min=ms_min, mpts_s=n / ms / 1e3, alg_bytes=B, gbs=B / ms / 1e6,
+                 frac_of_measured_hbm=B / ms / 1e6 / peak, variant=_native.last_variant(0), note=note)
+        results.append(r)
+        print(json.dumps(r), flush=True)
+
+    def want(name):
+        return not only or name in only
+
+    if want('cfg2a_grid'):
+        ms, mn = timed(lambda: f.eval(grid1m, ['dino_feats']), flush=flush)
+        rec('cfg2a_grid', 1_000_000, ms, mn, [(48, 64, 1024, 4)])
+    if want('cfg2a_scattered'):
+        ms, mn = timed(lambda: f.eval(scat1m, ['dino_feats']), flush=flush)
+        rec('cfg2a_scattered', 1_000_000, ms, mn, [(48, 64, 1024, 4)], 'N(0,0.25^2) keypoints, no locality')
+    if want('cfg5_frame'):
+        ms, mn = timed(lambda: f.eval(scat256k, ['dino_feats']), flush=flush)
+        rec('cfg5_frame_256k_scattered', 262144, ms, mn, [(48, 64, 1024, 4)])
+        comp = torch.randn(3, 1024, device=DEV); mean = torch.randn(1024, device=DEV)
+        ms, mn = timed(lambda: f.pca_project(f.eval(scat256k, ['dino_feats'])['dino_feats'], mean, comp), flush=flush)
+        rec('cfg5_frame_256k_eval+pca3', 262144, ms, mn, [(48, 64, 1024, 4)], 'eval then separate PCA(3) kernel')
+    if want('cfg3'):
+        ms, mn = timed(lambda: f.eval(grid1m, ['mask']), flush=flush)
+        rec('cfg3_mask_f32', 1_000_000, ms, mn, [(480, 640, 8, 4)])
+        ms, mn = timed(lambda: f.eval(grid1m, ['mask_u8']), flush=flush)
+        rec('cfg3_mask_u8', 1_000_000, ms, mn, [(480, 640, 8, 1)])
+        ms, mn = timed(lambda: f.eval(scat1m, ['mask_u8']), flush=flush)
+        rec('cfg3_mask_u8_scattered', 1_000_000, ms, mn, [(480, 640, 8, 1)])
+    if want('dist_only'):
+        ms, mn = timed(lambda: f.eval(grid1m, []), flush=flush)
+        rec('dist_only_1m', 1_000_000, ms, mn, [])
+        ms, mn = timed(lambda: f.eval(grid16m, []), flush=flush)
+        rec('dist_only_16m', 16_000_000, ms, mn, [])
+    if want('multi_key'):
+        ms, mn = timed(lambda: f.eval(grid1m, ['dino_feats', 'mask', 'color_tensor']), flush=flush)
+        rec('vis_repr_3keys', 1_000_000, ms, mn, [(48, 64, 1024, 4), (480, 640, 8, 4), (480, 640, 3, 4)],
+            'dino_feats+mask+color_tensor in one launch (reference vis_repr.py:103)')
+    if want('cfg2b'):
+        vol = f.curr_obs_torch['dino_feats']
+        try:
+            f.curr_obs_torch['dino_feats'] = torch.randn((V, 480, 640, 1024), device=DEV)
+            ms, mn = timed(lambda: f.eval(grid1m, ['dino_feats']), flush=flush, reps=5)
+            rec('cfg2b_fullres_volume', 1_000_000, ms, mn, [(480, 640, 1024, 4)], '5.03 GB volume, map (480,640)')
+        finally:
+            f.curr_obs_torch['dino_feats'] = vol
+    if want('torch_gpu'):
+        from oracle import torch_port as TP
+        obs = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in TP.obs_from_scene(sc).items()}
+        ms, mn = timed(lambda: TP.batch_eval(obs, H, W, grid1m, ['dino_feats']), warm=1, reps=3)
+        rec('torch_gpu_reference_ops_cfg2a', 1_000_000, ms, mn, [(48, 64, 1024, 4)],
+            'oracle/torch_port.py (reference operator sequence, 60k chunks) on the same B200')
+    with open(args.out, 'w') as fh:
+        for r in results:
+            fh.write(json.dumps(r) + '\n')
+
+
+if __name__ == '__main__':
+    main()
