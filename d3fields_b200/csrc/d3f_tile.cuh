@@ -43,21 +43,27 @@ struct TileSmem {
     int vis[TILE_PTS * TILE_V];
     float4 w4[TILE_PTS * TILE_V];     // folded corner weights per (point, view)
     int4 code[TILE_PTS];              // packed footprint codes of the 4 views of a point
+    int mask[TILE_PTS];               // bits 0-3: view sees the point; bits 4-7: its corner cell differs from
+                                      // the previous point's (or the previous point did not see it)
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// One view's contribution to a lane's 4 channels, with the corner cache.
-#define D3F_WIDE_VIEW(v, cv)                                                                       \
-    if ((cv) >= 0) {                                                                               \
-        if ((cv) != cur[v]) {                                                                      \
-            const float* b_ = vb + (size_t)(v) * vstride + (size_t)((cv) >> 2) * (size_t)C;        \
-            const int dx_ = ((cv) & 1) ? C : 0;                                                    \
-            const int dy_ = ((cv) & 2) ? rowC : 0;                                                 \
-            cc[v][0] = ldg4(b_); cc[v][1] = ldg4(b_ + dx_);                                        \
-            cc[v][2] = ldg4(b_ + dy_); cc[v][3] = ldg4(b_ + dy_ + dx_);                            \
-            cur[v] = (cv);                                                                         \
-        }                                                                                          \
+// Number of point runs a tile is split into for a map of S 128-channel slices (8 warps per CTA).
+__host__ __device__ inline int wide_runs(int S) { return S >= TILE_THREADS / 32 ? 1 : (TILE_THREADS / 32) / S; }
+__host__ __device__ inline int wide_run_len(int S) { const int R = wide_runs(S); return (TILE_PTS + R - 1) / R; }
+
+// Reload the four corner texels of view v (lane's 4 channels) from the packed footprint code.
+#define D3F_WIDE_RELOAD(v, cv)                                                                     \
+    {                                                                                              \
+        const float* b_ = vb + (size_t)(v) * vstride + (size_t)((cv) >> 2) * (size_t)C;            \
+        const int dx_ = ((cv) & 1) ? C : 0;                                                        \
+        const int dy_ = ((cv) & 2) ? rowC : 0;                                                     \
+        cc[v][0] = ldg4(b_); cc[v][1] = ldg4(b_ + dx_);                                            \
+        cc[v][2] = ldg4(b_ + dy_); cc[v][3] = ldg4(b_ + dy_ + dx_);                                \
+    }
+#define D3F_WIDE_FMA(v)                                                                            \
+    {                                                                                              \
         const float4 w_ = sm.w4[p * TILE_V + (v)];                                                 \
         fma4(acc, w_.x, cc[v][0]); fma4(acc, w_.y, cc[v][1]);                                      \
         fma4(acc, w_.z, cc[v][2]); fma4(acc, w_.w, cc[v][3]);                                      \
@@ -72,10 +78,9 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
     if (S >= nwarps) {                                      // every warp walks the whole tile on its slices
         s0 = warp; sstep = nwarps; p_begin = 0; p_end = npts;
     } else {                                                // fewer slices than warps: split the tile into runs
-        const int R = nwarps / S;
         const int r = warp / S;
-        if (r >= R) return;
-        const int run = (TILE_PTS + R - 1) / R;
+        if (r >= wide_runs(S)) return;
+        const int run = wide_run_len(S);
         s0 = warp - r * S; sstep = S;
         p_begin = r * run; p_end = min(p_begin + run, npts);
     }
@@ -86,14 +91,30 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
         const float* vb = vol + s * 128 + lane * 4;
         float* o = kp.out + (size_t)(tile0 + p_begin) * C + s * 128 + lane * 4;
         float4 cc[TILE_V][4];
-        int cur[TILE_V] = {-1, -1, -1, -1};
+#pragma unroll
+        for (int v = 0; v < TILE_V; ++v)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cc[v][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int m_next = (p_begin < p_end) ? sm.mask[p_begin] : 0;
         for (int p = p_begin; p < p_end; ++p, o += C) {
-            const int4 code = sm.code[p];
+            // the mask is the same in every lane; the OR-reduction moves it to a uniform register so the
+            // tests below are uniform branches (no divergence bookkeeping)
+            const unsigned m = __reduce_or_sync(0xffffffffu, (unsigned)m_next);
+            m_next = sm.mask[min(p + 1, TILE_PTS - 1)];
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            D3F_WIDE_VIEW(0, code.x)
-            D3F_WIDE_VIEW(1, code.y)
-            D3F_WIDE_VIEW(2, code.z)
-            D3F_WIDE_VIEW(3, code.w)
+            if (m != 0u) {
+                if (m & 0xF0u) {
+                    const int4 code = sm.code[p];
+                    if (m & 0x10u) D3F_WIDE_RELOAD(0, code.x)
+                    if (m & 0x20u) D3F_WIDE_RELOAD(1, code.y)
+                    if (m & 0x40u) D3F_WIDE_RELOAD(2, code.z)
+                    if (m & 0x80u) D3F_WIDE_RELOAD(3, code.w)
+                }
+                if (m & 1u) D3F_WIDE_FMA(0)
+                if (m & 2u) D3F_WIDE_FMA(1)
+                if (m & 4u) D3F_WIDE_FMA(2)
+                if (m & 8u) D3F_WIDE_FMA(3)
+            }
             __stcs(reinterpret_cast<float4*>(o), acc);
         }
     }
@@ -209,6 +230,24 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
         }
         __syncthreads();
         if (key_is_wide(ks.dtype[k], kp.C, kp.h, kp.w)) {
+            // per-point mask: which views see the point, and which of those changed texel cell since the
+            // previous point of the same run (a view the previous point did not see always reloads)
+            if (threadIdx.x < TILE_PTS) {
+                const int p = threadIdx.x;
+                const int run = wide_run_len(kp.C >> 7);
+                const int4 c = sm.code[p];
+                const bool first = (p % run) == 0;
+                const int4 q = first ? make_int4(-1, -1, -1, -1) : sm.code[p - 1];
+                unsigned m = 0;
+                if (p < npts) {
+                    if (c.x >= 0) m |= 0x01u | ((c.x != q.x) ? 0x10u : 0u);
+                    if (c.y >= 0) m |= 0x02u | ((c.y != q.y) ? 0x20u : 0u);
+                    if (c.z >= 0) m |= 0x04u | ((c.z != q.z) ? 0x40u : 0u);
+                    if (c.w >= 0) m |= 0x08u | ((c.w != q.w) ? 0x80u : 0u);
+                }
+                sm.mask[p] = (int)m;
+            }
+            __syncthreads();
             wide_accumulate(kp, tile0, npts, sm);
         } else {
             const bool vec4 = (kp.C % 4 == 0);

@@ -59,3 +59,30 @@ def test_torch_port_matches_reference_golden(name):
     g.check_exact('valid_mask', out['valid_mask'].numpy())
     for k in g.names:
         g.check_close(k, out[k].numpy())
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_c_oracle_matches_reference_golden_and_numpy_oracle(name):
+    """oracle/d3f_oracle.c: pinned against the reference's golden vectors, and equal to the numpy
+    restatement (bit-for-bit on dist/valid and on the per-view samples; the weighted mean only differs
+    through libm's expf vs numpy's exp)."""
+    from oracle import c_oracle as CO
+    g = Golden(name)
+    sc = g.scene
+    inter = not g.meta['batch']
+    out = CO.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, g.names, mu=g.mu, return_inter=inter)
+    g.check_exact('dist', out['dist'])
+    g.check_exact('valid_mask', out['valid_mask'])
+    for k in g.names:
+        g.check_close(k, out[k])
+        if inter:
+            g.check_close(k + '_inter', out[k + '_inter'])
+    od = CO.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, mu=g.mu, eval_dist=True)
+    g.check_exact('evaldist.dist', od['dist'])
+    g.check_exact('evaldist.valid_mask', od['valid_mask'])
+    if g.pts.shape[0] <= 40000:
+        ref = O.field_eval(g.pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, g.names, mu=g.mu, return_inter=inter)
+        for k in g.names:
+            if inter:
+                assert np.array_equal(out[k + '_inter'], ref[k + '_inter']), k
+            assert np.abs(out[k] - ref[k]).max() <= 1e-6 * max(1.0, np.abs(ref[k]).max())
