@@ -220,18 +220,21 @@ def main():
     pts = torch.from_numpy(pts_np).to(dev)
     names = ['dino_feats']
 
-    # in-place all-gather layout for the compact fields: every rank's kernel output is copied into its slot
+    # N > 1: in-place all-gather layout for the compact fields (d3fields_b200/sharded.py): the kernel writes the
+    # rank's dist / valid_mask straight into its slot of the gather buffers, then one all_gather per buffer
     if world > 1:
-        g_dist = torch.empty(world * n, dtype=torch.float32, device=dev)
-        g_valid = torch.empty(world * n, dtype=torch.uint8, device=dev)
+        g_dist = torch.empty((world, n), dtype=torch.float32, device=dev)
+        g_valid = torch.empty((world, n), dtype=torch.bool, device=dev)
+        slot = {'dist': g_dist[rank], 'valid_mask': g_valid[rank]}
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     def step():
-        out = f.eval(pts, return_names=names)
-        if world > 1:
-            dist.all_gather_into_tensor(g_dist, out['dist'])
-            dist.all_gather_into_tensor(g_valid, out['valid_mask'].view(torch.uint8))
+        if world == 1:
+            return f.eval(pts, return_names=names)
+        out = f.eval(pts, return_names=names, out=slot)
+        dist.all_gather_into_tensor(g_dist.view(-1), g_dist[rank])
+        dist.all_gather_into_tensor(g_valid.view(torch.uint8).view(-1), g_valid.view(torch.uint8)[rank])
         return out
 
     for _ in range(args.warmup):

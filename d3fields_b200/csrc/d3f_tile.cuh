@@ -42,9 +42,10 @@ struct TileSmem {
     float fac[TILE_PTS * TILE_V];
     int vis[TILE_PTS * TILE_V];
     float4 w4[TILE_PTS * TILE_V];     // folded corner weights per (point, view)
-    int4 code[TILE_PTS];              // packed footprint codes of the 4 views of a point
-    int mask[TILE_PTS];               // bits 0-3: view sees the point; bits 4-7: its corner cell differs from
-                                      // the previous point's (or the previous point did not see it)
+    int4 code[TILE_PTS + 4];          // packed footprint codes of the 4 views of a point
+    int mask[TILE_PTS + 4];           // bits 0-3: view sees the point; bits 4-7: its corner cell differs from
+                                      // the previous point's (or the previous point did not see it);
+                                      // bits 12-15: bits 4-7 of the point WIDE_LOOKAHEAD further on in the same run
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -54,21 +55,27 @@ __host__ __device__ inline int wide_runs(int S) { return S >= TILE_THREADS / 32 
 __host__ __device__ inline int wide_run_len(int S) { const int R = wide_runs(S); return (TILE_PTS + R - 1) / R; }
 
 // Reload the four corner texels of view v (lane's 4 channels) from the packed footprint code.
+// 32-bit element offsets: a view's map holds fewer than 2^31 elements (checked on the host).
 #define D3F_WIDE_RELOAD(v, cv)                                                                     \
     {                                                                                              \
-        const float* b_ = vb + (size_t)(v) * vstride + (size_t)((cv) >> 2) * (size_t)C;            \
-        const int dx_ = ((cv) & 1) ? C : 0;                                                        \
-        const int dy_ = ((cv) & 2) ? rowC : 0;                                                     \
+        const float* b_ = vbase[v] + (unsigned)((cv) >> 2) * (unsigned)C;                          \
+        const unsigned dx_ = ((cv) & 1) ? (unsigned)C : 0u;                                        \
+        const unsigned dy_ = ((cv) & 2) ? (unsigned)rowC : 0u;                                     \
         cc[v][0] = ldg4(b_); cc[v][1] = ldg4(b_ + dx_);                                            \
-        cc[v][2] = ldg4(b_ + dy_); cc[v][3] = ldg4(b_ + dy_ + dx_);                                \
+        cc[v][2] = ldg4(b_ + dy_); cc[v][3] = ldg4(b_ + (dy_ + dx_));                              \
     }
-#define D3F_WIDE_FMA(v)                                                                            \
+#define D3F_WIDE_FMA(v, w_)                                                                        \
     {                                                                                              \
-        const float4 w_ = sm.w4[p * TILE_V + (v)];                                                 \
         fma4(acc, w_.x, cc[v][0]); fma4(acc, w_.y, cc[v][1]);                                      \
         fma4(acc, w_.z, cc[v][2]); fma4(acc, w_.w, cc[v][3]);                                      \
     }
 
+constexpr int WIDE_LOOKAHEAD = 4;      // points between the L1 prefetch of a cell change and its reload
+
+// PREFETCH: bits 12-15 of a point's mask word say which views change cell WIDE_LOOKAHEAD points later; the warp
+// then prefetches its own 512-byte slice of those corner texels into L1, so the reload that follows is an L1 hit
+// instead of an L2 round trip with all eight warps of the CTA stalled on the same point.
+template <bool PREFETCH>
 __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmem& sm) {
     const int C = kp.C;
     const int S = C >> 7;                                   // 128-channel slices
@@ -84,25 +91,45 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
         s0 = warp - r * S; sstep = S;
         p_begin = r * run; p_end = min(p_begin + run, npts);
     }
+    if (p_end <= p_begin) return;
     const float* __restrict__ vol = static_cast<const float*>(kp.data);
     const size_t vstride = (size_t)kp.h * kp.w * C;
     const int rowC = kp.w * C;
     for (int s = s0; s < S; s += sstep) {
-        const float* vb = vol + s * 128 + lane * 4;
+        const float* vbase[TILE_V];
+#pragma unroll
+        for (int v = 0; v < TILE_V; ++v) vbase[v] = vol + (size_t)v * vstride + s * 128 + lane * 4;
         float* o = kp.out + (size_t)(tile0 + p_begin) * C + s * 128 + lane * 4;
         float4 cc[TILE_V][4];
 #pragma unroll
         for (int v = 0; v < TILE_V; ++v)
 #pragma unroll
             for (int q = 0; q < 4; ++q) cc[v][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int m_next = (p_begin < p_end) ? sm.mask[p_begin] : 0;
+        int m_next = sm.mask[p_begin];
         for (int p = p_begin; p < p_end; ++p, o += C) {
             // the mask is the same in every lane; the OR-reduction moves it to a uniform register so the
             // tests below are uniform branches (no divergence bookkeeping)
             const unsigned m = __reduce_or_sync(0xffffffffu, (unsigned)m_next);
-            m_next = sm.mask[min(p + 1, TILE_PTS - 1)];
+            m_next = sm.mask[p + 1];                                   // the array is padded by one
+            if (PREFETCH && (m & 0xF000u)) {
+                const int4 code = sm.code[p + WIDE_LOOKAHEAD];
+                const int cvs[4] = {code.x, code.y, code.z, code.w};
+#pragma unroll
+                for (int v = 0; v < TILE_V; ++v) {
+                    if (m & (0x1000u << v)) {
+                        const int cv = cvs[v];
+                        const float* b_ = vbase[v] + (unsigned)(cv >> 2) * (unsigned)C;
+                        const unsigned dx_ = (cv & 1) ? (unsigned)C : 0u;
+                        const unsigned dy_ = (cv & 2) ? (unsigned)rowC : 0u;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(b_));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(b_ + dx_));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(b_ + dy_));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(b_ + (dy_ + dx_)));
+                    }
+                }
+            }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m != 0u) {
+            if (m & 0xFFu) {
                 if (m & 0xF0u) {
                     const int4 code = sm.code[p];
                     if (m & 0x10u) D3F_WIDE_RELOAD(0, code.x)
@@ -110,10 +137,16 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
                     if (m & 0x40u) D3F_WIDE_RELOAD(2, code.z)
                     if (m & 0x80u) D3F_WIDE_RELOAD(3, code.w)
                 }
-                if (m & 1u) D3F_WIDE_FMA(0)
-                if (m & 2u) D3F_WIDE_FMA(1)
-                if (m & 4u) D3F_WIDE_FMA(2)
-                if (m & 8u) D3F_WIDE_FMA(3)
+                // the weight reads of every visible view are issued before the first FMA
+                float4 w0, w1, w2, w3;
+                if (m & 1u) w0 = sm.w4[p * TILE_V + 0];
+                if (m & 2u) w1 = sm.w4[p * TILE_V + 1];
+                if (m & 4u) w2 = sm.w4[p * TILE_V + 2];
+                if (m & 8u) w3 = sm.w4[p * TILE_V + 3];
+                if (m & 1u) D3F_WIDE_FMA(0, w0)
+                if (m & 2u) D3F_WIDE_FMA(1, w1)
+                if (m & 4u) D3F_WIDE_FMA(2, w2)
+                if (m & 8u) D3F_WIDE_FMA(3, w3)
             }
             __stcs(reinterpret_cast<float4*>(o), acc);
         }
@@ -155,10 +188,10 @@ __device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t t
 
 // wide-path eligibility of one key (host and device agree through this one function)
 __host__ __device__ inline bool key_is_wide(int dtype, int C, int h, int w) {
-    return dtype == D3F_F32 && (C % 128) == 0 && (long long)h * w < (1ll << 29);
+    return dtype == D3F_F32 && (C % 128) == 0 && (long long)h * w < (1ll << 29) && (long long)h * w * C < (1ll << 31);
 }
 
-template <bool RECIP>
+template <bool RECIP, int VARIANT>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 field_tile_kernel(const EvalParams ep, const KeySet ks) {
     __shared__ TileSmem sm;
@@ -246,9 +279,23 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
                     if (c.w >= 0) m |= 0x08u | ((c.w != q.w) ? 0x80u : 0u);
                 }
                 sm.mask[p] = (int)m;
+            } else if (threadIdx.x < TILE_PTS + 4) {
+                sm.mask[threadIdx.x] = 0;
+            }
+            if (VARIANT & 4) {
+                __syncthreads();
+                int ahead = 0;
+                if (threadIdx.x < TILE_PTS) {
+                    const int p = threadIdx.x;
+                    const int run = wide_run_len(kp.C >> 7);
+                    if ((p % run) + WIDE_LOOKAHEAD < run && p + WIDE_LOOKAHEAD < TILE_PTS)
+                        ahead = (sm.mask[p + WIDE_LOOKAHEAD] & 0xF0) << 8;
+                }
+                __syncthreads();
+                if (threadIdx.x < TILE_PTS) sm.mask[threadIdx.x] |= ahead;
             }
             __syncthreads();
-            wide_accumulate(kp, tile0, npts, sm);
+            wide_accumulate<(VARIANT & 4) != 0>(kp, tile0, npts, sm);
         } else {
             const bool vec4 = (kp.C % 4 == 0);
             if (ks.dtype[k] == D3F_F32) {

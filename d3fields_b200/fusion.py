@@ -178,7 +178,7 @@ class Fusion:
             raise ValueError("index_rounding must be 'cpu' or 'cuda'")
         return f
 
-    def _run(self, pts, return_names, return_inter, eval_dist):
+    def _run(self, pts, return_names, return_inter, eval_dist, out=None):
         self._check_pts(pts)
         names = list(return_names)
         V, H, W, pose_p, K_p, depth_p = self._obs_ptrs()
@@ -189,15 +189,23 @@ class Fusion:
             keep.append(vol)
         n = int(pts.shape[0])
         if not pts.is_cuda:
-            return self._run_host(pts, names, keys, V, H, W, pose_p, K_p, depth_p, eval_dist)
+            return self._run_host(pts, names, keys, V, H, W, pose_p, K_p, depth_p, eval_dist, out=out)
         dev = self.curr_obs_torch['depth'].device
         if pts.device != dev:
             raise ValueError(f'pts is on {pts.device} but the observation is on {dev}')
         pts = pts.contiguous()
         with torch.cuda.device(dev):
-            dist = torch.empty(n, dtype=torch.float32, device=dev)
-            valid = torch.empty(n, dtype=torch.bool, device=dev)
-            outs = [torch.empty((n, kt[4]), dtype=torch.float32, device=dev) for kt in keys]
+            def buf(name, shape, dtype):
+                if out is not None and name in out:          # caller-owned output (e.g. a slot of a gather buffer)
+                    t = out[name]
+                    if tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_contiguous() or t.device != dev:
+                        raise ValueError(f"out['{name}'] must be a contiguous {dtype} tensor of shape {tuple(shape)} on {dev}")
+                    return t
+                return torch.empty(shape, dtype=dtype, device=dev)
+
+            dist = buf('dist', (n,), torch.float32)
+            valid = buf('valid_mask', (n,), torch.bool)
+            outs = [buf(k, (n, kt[4]), torch.float32) for k, kt in zip(names, keys)]
             inters = [torch.empty((V, n, kt[4]), dtype=torch.float32, device=dev) for kt in keys] if return_inter else None
             stream = torch.cuda.current_stream(dev).cuda_stream
             _native.eval_device(V, H, W, pose_p, K_p, depth_p, pts.data_ptr(), n, keys,
@@ -238,13 +246,14 @@ class Fusion:
             res[k] = o
         return res
 
-    def eval(self, pts, return_names=['dino_feats', 'mask'], return_inter=False):
+    def eval(self, pts, return_names=['dino_feats', 'mask'], return_inter=False, out=None):
         """(N,3) world points -> {'dist' (N,), 'valid_mask' (N,) bool, '<k>' (N,C_k) for k in return_names
         [, '<k>_inter' (V,N,C_k)]}.  Reference fusion.py:305-394.  CPU `pts` give CPU results through the
-        host-buffer entry point (return_inter is device-only)."""
+        host-buffer entry point (return_inter is device-only).  `out` (an extension) may hold preallocated
+        tensors for 'dist' / 'valid_mask' / any name; the kernel writes them in place."""
         if isinstance(pts, torch.Tensor) and not pts.is_cuda and return_inter:
             raise ValueError('return_inter needs device points')
-        return self._run(pts, return_names, return_inter, eval_dist=False)
+        return self._run(pts, return_names, return_inter, eval_dist=False, out=out)
 
     def eval_dist(self, pts):
         """Unclamped signed distance: {'dist', 'valid_mask'}.  Reference fusion.py:396-436."""

@@ -268,3 +268,25 @@ def test_device_grid_matches_create_init_grid():
                         torch.cuda.current_stream().cuda_stream)
     d = (pts.cpu() - ref).abs().max().item()
     assert d <= 6e-8, d            # torch.arange's vectorised path may differ from the scalar formula by 1 ulp
+
+
+def test_sharded_helper_single_rank_writes_in_place():
+    """world_size 1 path of d3fields_b200.sharded.eval_sharded over the CUDA kernels: same results as eval, and
+    the gathered keys are the buffers the kernel wrote (no copy before the collective)."""
+    from d3fields_b200.sharded import eval_sharded
+    sc = S.make_scene(4, 120, 160, seed=31, feat=(12, 16, 128), num_inst=4)
+    pts = torch.from_numpy(S.grid_points(25, 25, 25)).to(DEV)
+    f = make_fusion(sc, DEV)
+    seen = {}
+
+    def eval_fn(local, names, out):
+        r = f.eval(local, return_names=names, out=out)
+        seen.update({k: (r[k].data_ptr(), out[k].data_ptr()) for k in out})
+        return r
+
+    got = eval_sharded(eval_fn, pts, ['dino_feats', 'mask'], gather=('dist', 'valid_mask', 'mask'), channels={'mask': 4})
+    ref = f.eval(pts, return_names=['dino_feats', 'mask'])
+    assert got['shard'] == (0, len(pts))
+    assert all(a == b for a, b in seen.values())
+    for k in ('dist', 'valid_mask', 'mask', 'dino_feats'):
+        assert torch.equal(got[k], ref[k]), k

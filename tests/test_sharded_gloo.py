@@ -1,0 +1,82 @@
+"""CPU, world_size 2 and 3 over gloo: the N>1 host logic — slab partition, in-place gather layout, ragged
+slabs, replication of the observation.  The per-slab evaluation is the CPU oracle here (tests may call it);
+on the GPU box tests/test_parity_gpu.py::test_sharded_* runs the same helper over the CUDA kernels."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from d3fields_b200 import scene as S
+from d3fields_b200.sharded import broadcast_observation, eval_sharded, shard_range, slab_capacity
+
+
+def test_shard_ranges_tile_the_points():
+    for n in (0, 1, 7, 128, 1000, 1_000_003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1 and slab_capacity(n, world) == max(sizes)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from oracle import field_oracle as O
+        sc = S.make_scene(2, 60, 80, seed=5, feat=(6, 8, 8), num_inst=3)
+        obs = {'pose': torch.from_numpy(sc.pose), 'K': torch.from_numpy(sc.K), 'depth': torch.from_numpy(sc.depth),
+               'mask': torch.from_numpy(sc.maps['mask']), 'dino_feats': torch.from_numpy(sc.maps['dino_feats'])}
+        if rank != 0:                      # only rank 0 "ran update()": the others receive the observation
+            for v in obs.values():
+                v.zero_()
+        broadcast_observation(obs, src=0)
+        assert torch.equal(obs['depth'], torch.from_numpy(sc.depth))
+        pts = torch.from_numpy(S.scattered_points(n, 9))
+        maps = {'mask': obs['mask'].numpy(), 'dino_feats': obs['dino_feats'].numpy()}
+
+        def eval_fn(local, names, out):
+            r = O.field_eval(local.numpy(), obs['pose'].numpy(), obs['K'].numpy(), obs['depth'].numpy(), 60, 80, maps, names)
+            res = {k: torch.from_numpy(v) for k, v in r.items()}
+            if rank == 0:                  # one rank honours `out` (in-place slot), the other returns fresh tensors
+                for k in out:
+                    out[k].copy_(res[k]); res[k] = out[k]
+            return res
+
+        got = eval_sharded(eval_fn, pts, ['dino_feats', 'mask'], gather=('dist', 'valid_mask', 'mask'), channels={'mask': 3})
+        full = O.field_eval(pts.numpy(), sc.pose, sc.K, sc.depth, 60, 80, sc.maps, ['dino_feats', 'mask'])
+        s, e = got['shard']
+        assert (s, e) == shard_range(n, rank, world)
+        ok = (np.array_equal(got['dist'].numpy(), full['dist']) and np.array_equal(got['valid_mask'].numpy(), full['valid_mask'])
+              and np.array_equal(got['mask'].numpy(), full['mask']) and np.array_equal(got['dino_feats'].numpy(), full['dino_feats'][s:e])
+              and got['dist'].shape == (n,) and got['mask'].shape == (n, 3))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n', [(2, 1000), (2, 1001), (3, 500)])
+def test_sharded_eval_over_gloo(world, n):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0, f'worker exit code {p.exitcode}'
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert res == {r: True for r in range(world)}
