@@ -38,7 +38,8 @@ class D3FObs(C.Structure):
 
 
 class D3FKey(C.Structure):
-    _fields_ = [('data', C.c_void_p), ('dtype', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('C', C.c_int32)]
+    _fields_ = [('data', C.c_void_p), ('dtype', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('C', C.c_int32),
+                ('bias', C.c_void_p)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -103,8 +104,8 @@ def _ptr_array(ptrs: Sequence[Optional[int]]):
 
 def _keys_array(keys: Sequence[tuple]):
     arr = (D3FKey * max(len(keys), 1))()
-    for i, (data, dtype, h, w, c) in enumerate(keys):
-        arr[i] = D3FKey(data, dtype, h, w, c)
+    for i, key in enumerate(keys):          # (data_ptr, dtype, h, w, C[, bias_ptr])
+        arr[i] = D3FKey(key[0], key[1], key[2], key[3], key[4], key[5] if len(key) > 5 else None)
     return arr
 
 

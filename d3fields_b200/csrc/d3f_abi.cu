@@ -70,6 +70,8 @@ int validate(const D3FObs* obs, const void* pts, int64_t n, const D3FKey* keys, 
         if (q.h < 1 || q.w < 1 || q.C < 1) return fail(D3F_EINVAL, "keys[%d] shape (%d,%d,%d) invalid", k, q.h, q.w, q.C);
         if ((int64_t)q.h * q.w >= (1ll << 31)) return fail(D3F_EINVAL, "keys[%d] map too large", k);
         if (n > 0 && !out[k]) return fail(D3F_EINVAL, "out[%d] is NULL", k);
+        if (q.bias && q.C >= 128) return fail(D3F_EINVAL, "keys[%d].bias is supported for C < 128 only", k);
+        if (q.bias && q.C % 4 == 0 && !aligned(q.bias, 16)) return fail(D3F_EINVAL, "keys[%d].bias must be 16-byte aligned", k);
     }
     return D3F_OK;
 }
@@ -95,6 +97,7 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
         ks.k[k].inter = (out_inter && out_inter[k]) ? out_inter[k] : nullptr;
         ks.k[k].h = keys[k].h; ks.k[k].w = keys[k].w; ks.k[k].C = keys[k].C;
         ks.dtype[k] = keys[k].dtype;
+        ks.k[k].bias = keys[k].bias;
         any_inter |= ks.k[k].inter != nullptr;
         if (keys[k].C % 4 == 0) {
             const size_t a_in = keys[k].dtype == D3F_F32 ? 16 : 4;
@@ -120,12 +123,15 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
             if (d3f::key_is_wide(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w))
                 wide_bytes += (size_t)obs->V * keys[k].h * keys[k].w * keys[k].C * 4;
         const bool prefetch = force >= 0 ? force != 0 : wide_bytes > (size_t)(64u << 20);
-        if (recip) {
-            if (prefetch) d3f::field_tile_kernel<true, 4><<<grid, block, 0, st>>>(ep, ks);
-            else          d3f::field_tile_kernel<true, 0><<<grid, block, 0, st>>>(ep, ks);
+        if (wide_bytes == 0) {            // no register-cached walk needed: the light instantiation (4 CTAs/SM)
+            if (recip) d3f::field_tile_kernel<true, 0, false><<<grid, block, 0, st>>>(ep, ks);
+            else       d3f::field_tile_kernel<false, 0, false><<<grid, block, 0, st>>>(ep, ks);
+        } else if (recip) {
+            if (prefetch) d3f::field_tile_kernel<true, 4, true><<<grid, block, 0, st>>>(ep, ks);
+            else          d3f::field_tile_kernel<true, 0, true><<<grid, block, 0, st>>>(ep, ks);
         } else {
-            if (prefetch) d3f::field_tile_kernel<false, 4><<<grid, block, 0, st>>>(ep, ks);
-            else          d3f::field_tile_kernel<false, 0><<<grid, block, 0, st>>>(ep, ks);
+            if (prefetch) d3f::field_tile_kernel<false, 4, true><<<grid, block, 0, st>>>(ep, ks);
+            else          d3f::field_tile_kernel<false, 0, true><<<grid, block, 0, st>>>(ep, ks);
         }
         g_launches.fetch_add(1, std::memory_order_relaxed);
         D3F_CUDA(cudaGetLastError());
@@ -266,7 +272,7 @@ int d3f_pca_project(const float* x, int64_t n, int32_t C, const float* mean, con
                     int32_t n_comp, float* y, void* stream) {
     if (n < 0 || C < 1 || n_comp < 1 || n_comp > d3f::PCA_MAX_COMP)
         return fail(D3F_EINVAL, "pca: n=%lld C=%d n_comp=%d (n_comp must be 1..%d)", (long long)n, C, n_comp, d3f::PCA_MAX_COMP);
-    if (n > 0 && (!x || !mean || !components || !y)) return fail(D3F_EINVAL, "pca: NULL pointer");
+    if (n > 0 && (!x || !components || !y)) return fail(D3F_EINVAL, "pca: NULL pointer");
     int rc = check_device();
     if (rc) return rc;
     if (n == 0) return D3F_OK;

@@ -6,7 +6,7 @@ namespace d3f {
 
 constexpr int PCA_MAX_COMP = 8;
 
-// y[i, j] = sum_c (x[i,c] - mean[c]) * comp[j,c]  — sklearn PCA.transform as the reference applies it
+// y[i, j] = sum_c (x[i,c] - mean[c]) * comp[j,c] (mean may be null: plain x @ comp^T)  — sklearn PCA.transform as the reference applies it
 // to eval()'s descriptors (reference fusion.py:1386-1392).  One warp per row: lanes stride the
 // channels (coalesced 128-bit loads when C % 4 == 0), one accumulator per component, butterfly
 // reduction.  HBM-bound on reading x once (4*C bytes per row).
@@ -25,7 +25,7 @@ pca_project_kernel(const float* __restrict__ x, int64_t n, int C, const float* _
     if (vec) {
         for (int c = lane * 4; c < C; c += 128) {
             const float4 xv = __ldcs(reinterpret_cast<const float4*>(xr + c));
-            const float4 mv = __ldg(reinterpret_cast<const float4*>(mean + c));
+            const float4 mv = mean ? __ldg(reinterpret_cast<const float4*>(mean + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 d = make_float4(xv.x - mv.x, xv.y - mv.y, xv.z - mv.z, xv.w - mv.w);
 #pragma unroll
             for (int j = 0; j < PCA_MAX_COMP; ++j) {
@@ -38,7 +38,7 @@ pca_project_kernel(const float* __restrict__ x, int64_t n, int C, const float* _
         }
     } else {
         for (int c = lane; c < C; c += 32) {
-            const float d = xr[c] - __ldg(mean + c);
+            const float d = xr[c] - (mean ? __ldg(mean + c) : 0.f);
 #pragma unroll
             for (int j = 0; j < PCA_MAX_COMP; ++j)
                 if (j < n_comp) acc[j] = fmaf(d, __ldg(comp + (size_t)j * C + c), acc[j]);

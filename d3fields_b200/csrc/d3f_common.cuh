@@ -31,6 +31,7 @@ struct KeyParams {
     const void* __restrict__ data;      // (V,h,w,C)
     float* __restrict__ out;            // (n,C)
     float* __restrict__ inter;          // (V,n,C) or nullptr
+    const float* __restrict__ bias;     // nullptr, or (C): subtracted from every output row (narrow keys only)
     int32_t h, w, C;
 };
 

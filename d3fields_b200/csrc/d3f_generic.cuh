@@ -94,6 +94,14 @@ __device__ __forceinline__ void generic_accumulate(const KeyParams& kp, int V, i
                 acc.x = fmaf(fac, r, acc.x);
             }
         }
+        if (kp.bias) {                                   // affine epilogue: out = field - bias
+            if (VEC == 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(kp.bias + c));
+                acc.x -= b.x; acc.y -= b.y; acc.z -= b.z; acc.w -= b.w;
+            } else {
+                acc.x -= __ldg(kp.bias + c);
+            }
+        }
         float* o = kp.out + (size_t)(tile0 + p) * C + c;
         if (VEC == 4) __stcs(reinterpret_cast<float4*>(o), acc);
         else          __stcs(o, acc.x);

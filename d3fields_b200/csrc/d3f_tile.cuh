@@ -180,6 +180,14 @@ __device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t t
                 acc.x = fmaf(w.z, Load4<T>::ld1(b + dy), acc.x); acc.x = fmaf(w.w, Load4<T>::ld1(b + dy + dx), acc.x);
             }
         }
+        if (kp.bias) {                                   // affine epilogue: out = field - bias (PCA mean term)
+            if (VEC == 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(kp.bias + c));
+                acc.x -= b.x; acc.y -= b.y; acc.z -= b.z; acc.w -= b.w;
+            } else {
+                acc.x -= __ldg(kp.bias + c);
+            }
+        }
         float* o = kp.out + (size_t)(tile0 + p) * C + c;
         if (VEC == 4) __stcs(reinterpret_cast<float4*>(o), acc);
         else          __stcs(o, acc.x);
@@ -191,8 +199,11 @@ __host__ __device__ inline bool key_is_wide(int dtype, int C, int h, int w) {
     return dtype == D3F_F32 && (C % 128) == 0 && (long long)h * w < (1ll << 29) && (long long)h * w * C < (1ll << 31);
 }
 
-template <bool RECIP, int VARIANT>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+// WIDE=false compiles the register-cached walk out: launches with only narrow keys (instance masks, colours,
+// PCA-projected volumes) or no keys at all (dist / valid_mask sweeps) then need ~60 registers and run 4 CTAs
+// per SM instead of 2.
+template <bool RECIP, int VARIANT, bool WIDE>
+__global__ void __launch_bounds__(TILE_THREADS, WIDE ? 2 : 4)
 field_tile_kernel(const EvalParams ep, const KeySet ks) {
     __shared__ TileSmem sm;
     const int V = ep.V;
@@ -262,7 +273,7 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
             codes[s] = code;
         }
         __syncthreads();
-        if (key_is_wide(ks.dtype[k], kp.C, kp.h, kp.w)) {
+        if (WIDE && key_is_wide(ks.dtype[k], kp.C, kp.h, kp.w)) {
             // per-point mask: which views see the point, and which of those changed texel cell since the
             // previous point of the same run (a view the previous point did not see always reloads)
             if (threadIdx.x < TILE_PTS) {

@@ -274,19 +274,60 @@ class Fusion:
         keys = [self._key_tuple(k, V)[0] for k in names]
         return self._run_host(pts, names, keys, V, H, W, pose_p, K_p, depth_p, False, out=out)
 
+    def eval_pca(self, pts, name, mean, components):
+        """eval(pts, [name])[name] followed by sklearn's PCA.transform, (row - mean) @ components.T (what the
+        reference does on the host after eval, fusion.py:1386-1392) — without ever forming the (N,C) field.
+
+        The field is linear in the sampled map, so the map is projected first (V*h*w rows instead of N) and the
+        k-channel result is queried through the narrow path with bias = mean @ components.T:
+            (field - mean) @ W^T  ==  field_of(map @ W^T) - mean @ W^T.
+        Returns {'dist', 'valid_mask', name + '_pca' (N,k)}."""
+        self._check_pts(pts)
+        V, H, W, pose_p, K_p, depth_p = self._obs_ptrs()
+        vol = self.curr_obs_torch[name]
+        if not (isinstance(vol, torch.Tensor) and vol.dim() == 4 and vol.is_cuda and vol.is_contiguous()
+                and vol.dtype == torch.float32 and vol.shape[0] == V):
+            raise ValueError(f"curr_obs_torch['{name}'] must be a contiguous float32 CUDA (V,h,w,C) tensor")
+        dev = vol.device
+        if not pts.is_cuda or pts.device != dev:
+            raise ValueError(f'pts must be on {dev}')
+        _, h, w, C = (int(x) for x in vol.shape)
+        mean = _as_device(mean, dev, torch.float32).contiguous().reshape(1, C)
+        comp = _as_device(components, dev, torch.float32).contiguous()
+        k = int(comp.shape[0])
+        if tuple(comp.shape) != (k, C) or not (1 <= k <= 8):
+            raise ValueError(f'components must be (k,{C}) with 1 <= k <= 8')
+        n = int(pts.shape[0])
+        pts = pts.contiguous()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            proj = torch.empty((V, h, w, k), dtype=torch.float32, device=dev)
+            bias = torch.empty((1, k), dtype=torch.float32, device=dev)
+            _native.pca_project(vol.data_ptr(), V * h * w, C, None, comp.data_ptr(), k, proj.data_ptr(), stream)
+            _native.pca_project(mean.data_ptr(), 1, C, None, comp.data_ptr(), k, bias.data_ptr(), stream)
+            dist = torch.empty(n, dtype=torch.float32, device=dev)
+            valid = torch.empty(n, dtype=torch.bool, device=dev)
+            y = torch.empty((n, k), dtype=torch.float32, device=dev)
+            _native.eval_device(V, H, W, pose_p, K_p, depth_p, pts.data_ptr(), n,
+                                [(proj.data_ptr(), _native.D3F_F32, h, w, k, bias.data_ptr())],
+                                dist.data_ptr(), valid.data_ptr(), [y.data_ptr()], None,
+                                self._flags(False), float(self.mu), stream)
+        return {'dist': dist, 'valid_mask': valid, name + '_pca': y}
+
     # ------------------------------------------------------------------ descriptors -> PCA
     def pca_project(self, feats, mean, components):
         """(feats - mean) @ components.T on the device: sklearn PCA.transform as the reference applies it
         to descriptors on the host (fusion.py:1386-1392).  feats (N,C), mean (C,), components (k,C)."""
         dev = feats.device
-        mean = _as_device(mean, dev, torch.float32).contiguous()
+        mean = _as_device(mean, dev, torch.float32).contiguous() if mean is not None else None
         components = _as_device(components, dev, torch.float32).contiguous()
         feats = feats.contiguous()
         n, c = feats.shape
         k = components.shape[0]
         y = torch.empty((n, k), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _native.pca_project(feats.data_ptr(), n, c, mean.data_ptr(), components.data_ptr(), k, y.data_ptr(),
+            _native.pca_project(feats.data_ptr(), n, c, mean.data_ptr() if mean is not None else None,
+                                components.data_ptr(), k, y.data_ptr(),
                                 torch.cuda.current_stream(dev).cuda_stream)
         return y
 

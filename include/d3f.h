@@ -67,6 +67,11 @@ typedef struct D3FKey {
     const void* data;     /* (V,h,w,C) channels-last, contiguous */
     int32_t dtype;        /* D3F_F32 | D3F_U8 */
     int32_t h, w, C;
+    const float* bias;    /* NULL, or (C) device floats subtracted from every output row (C < 128 only).
+                             Used for PCA'd descriptor fields: because the field is linear in the sampled map,
+                             (field - mean) @ W^T == field_of(map @ W^T) - mean @ W^T, so the map is projected
+                             once with d3f_pca_project and queried as a C = n_comp key with bias = mean @ W^T
+                             (reference fusion.py:1386-1392 does the projection on the host, after eval). */
 } D3FKey;
 
 /* Replaces Fusion.eval (reference fusion.py:305-394), and with D3F_FLAG_EVAL_DIST
@@ -104,7 +109,7 @@ int d3f_eval_host(const D3FObs* obs, const float* pts_host, int64_t n,
 /* Fused PCA projection of a descriptor field: y = (x - mean) @ components^T, the
  * sklearn.decomposition.PCA.transform the reference applies on the host to eval's
  * 'dino_feats' (reference fusion.py:1386-1392, weights from pca_model/*.pkl).
- *   x (n,C) device, mean (C) device, components (n_comp,C) device, y (n,n_comp) device. */
+ *   x (n,C) device, mean (C) device or NULL (no centring), components (n_comp,C) device, y (n,n_comp) device. */
 int d3f_pca_project(const float* x, int64_t n, int32_t C,
                     const float* mean, const float* components, int32_t n_comp,
                     float* y, void* stream);

@@ -290,3 +290,31 @@ def test_sharded_helper_single_rank_writes_in_place():
     assert all(a == b for a, b in seen.values())
     for k in ('dist', 'valid_mask', 'mask', 'dino_feats'):
         assert torch.equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize('C,k', [(1024, 3), (256, 4), (128, 1), (64, 8), (7, 2)])
+def test_pca_field_via_projected_volume(C, k):
+    """Fusion.eval_pca == eval(..)[name] followed by sklearn-style (x - mean) @ components.T (reference
+    fusion.py:1386-1392).  The kernel samples the PROJECTED volume (linearity of the field in the map)."""
+    sc = S.make_scene(4, 240, 320, seed=41, feat=(24, 32, C))
+    pts_np = np.concatenate([S.grid_points(30, 30, 30), S.scattered_points(5000, 41), S.adversarial_points(sc, 41, 8)])
+    pts = torch.from_numpy(pts_np).to(DEV)
+    rs = np.random.RandomState(7)
+    mean = rs.standard_normal(C).astype(np.float32)
+    comp = (rs.standard_normal((k, C)) / np.sqrt(C)).astype(np.float32)
+    f = make_fusion(sc, DEV)
+    got = f.eval_pca(pts, 'dino_feats', mean, comp)
+    assert _native.last_variant(0) == 'tile/narrow'
+    ref = f.eval(pts, return_names=['dino_feats'])
+    assert torch.equal(got['dist'], ref['dist']) and torch.equal(got['valid_mask'], ref['valid_mask'])
+    x = ref['dino_feats'].cpu().numpy().astype(np.float64)
+    y = (x - mean.astype(np.float64)) @ comp.T.astype(np.float64)
+    g = got['dino_feats_pca'].cpu().numpy()
+    assert g.shape == (len(pts_np), k)
+    assert np.abs(g - y).max() <= 1e-4 * np.abs(y).max()
+    none = ~ref['valid_mask'].cpu().numpy()
+    base = -(mean.astype(np.float64) @ comp.T.astype(np.float64))
+    assert np.abs(g[none] - base).max() <= 1e-5 * max(1.0, np.abs(base).max())
+    # plain projection kernel without centring
+    z = f.pca_project(ref['dino_feats'], None, comp).cpu().numpy()
+    assert np.abs(z - x @ comp.T.astype(np.float64)).max() <= 1e-4 * max(1e-6, np.abs(x @ comp.T).max())

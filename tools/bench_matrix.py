@@ -87,6 +87,14 @@ def main():
         comp = torch.randn(3, 1024, device=DEV); mean = torch.randn(1024, device=DEV)
         ms, mn = timed(lambda: f.pca_project(f.eval(scat256k, ['dino_feats'])['dino_feats'], mean, comp), flush=flush)
         rec('cfg5_frame_256k_eval+pca3', 262144, ms, mn, [(48, 64, 1024, 4)], 'eval then separate PCA(3) kernel')
+        ms, mn = timed(lambda: f.eval_pca(scat256k, 'dino_feats', mean, comp), flush=flush)
+        r = dict(name='cfg5_frame_256k_pca3_projected_volume', n=262144, ms=ms, ms_min=mn, mpts_s=262144 / ms / 1e3,
+                 variant=_native.last_variant(0), note='PCA(3) of the field via the projected volume (narrow path): 12 B/pt out instead of 4 KB/pt')
+        results.append(r); print(json.dumps(r), flush=True)
+        ms, mn = timed(lambda: f.eval_pca(grid1m, 'dino_feats', mean, comp), flush=flush)
+        r = dict(name='cfg2a_grid_pca3_projected_volume', n=1000000, ms=ms, ms_min=mn, mpts_s=1000000 / ms / 1e3,
+                 variant=_native.last_variant(0), note='1M grid points, PCA(3) via projected volume')
+        results.append(r); print(json.dumps(r), flush=True)
     if want('cfg3'):
         ms, mn = timed(lambda: f.eval(grid1m, ['mask']), flush=flush)
         rec('cfg3_mask_f32', 1_000_000, ms, mn, [(480, 640, 8, 4)])
