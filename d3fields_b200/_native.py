@@ -18,7 +18,7 @@ FLAG_EVAL_DIST, FLAG_RECIP_NORM = 1, 2
 ABI_VERSION = 1
 
 # every symbol include/d3f.h declares (tests check the built library exports exactly these)
-SYMBOLS = ('d3f_eval', 'd3f_eval_host', 'd3f_pca_project', 'd3f_create_grid', 'd3f_abi_version',
+SYMBOLS = ('d3f_eval', 'd3f_eval_host', 'd3f_eval_backward', 'd3f_pca_project', 'd3f_create_grid', 'd3f_abi_version',
            'd3f_last_error', 'd3f_launch_count', 'd3f_last_variant')
 
 
@@ -74,6 +74,8 @@ def load() -> C.CDLL:
     lib.d3f_eval_host.argtypes = [C.POINTER(D3FObs), vp, i64, C.POINTER(D3FKey), i32, vp, vp,
                                   C.POINTER(vp), u32, f32]
     lib.d3f_eval_host.restype = C.c_int
+    lib.d3f_eval_backward.argtypes = [C.POINTER(D3FObs), vp, i64, C.POINTER(D3FKey), i32, C.POINTER(vp), vp, vp, u32, f32, vp]
+    lib.d3f_eval_backward.restype = C.c_int
     lib.d3f_pca_project.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp]
     lib.d3f_pca_project.restype = C.c_int
     lib.d3f_create_grid.argtypes = [f64, f64, f64, f64, i32, i32, i32, vp, vp]
@@ -127,6 +129,15 @@ def eval_host(V: int, H: int, W: int, pose: int, K: int, depth: int, pts_host: i
     obs = D3FObs(V, H, W, pose, K, depth)
     _check(lib.d3f_eval_host(C.byref(obs), pts_host, n, _keys_array(keys), len(keys), dist_host, valid_host,
                              _ptr_array(outs_host), flags, mu))
+
+
+def eval_backward(V: int, H: int, W: int, pose: int, K: int, depth: int, pts: int, n: int, keys: Sequence[tuple],
+                  grad_outs: Sequence[Optional[int]], grad_dist: Optional[int], grad_pts: int, flags: int, mu: float,
+                  stream: int) -> None:
+    lib = load()
+    obs = D3FObs(V, H, W, pose, K, depth)
+    _check(lib.d3f_eval_backward(C.byref(obs), pts, n, _keys_array(keys), len(keys), _ptr_array(grad_outs),
+                                 grad_dist, grad_pts, flags, mu, stream))
 
 
 def pca_project(x: int, n: int, c: int, mean: int, comp: int, n_comp: int, y: int, stream: int) -> None:

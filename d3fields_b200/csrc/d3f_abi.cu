@@ -14,6 +14,7 @@
 #include "d3f_generic.cuh"
 #include "d3f_tile.cuh"
 #include "d3f_aux.cuh"
+#include "d3f_backward.cuh"
 
 namespace {
 
@@ -265,6 +266,44 @@ int d3f_eval_host(const D3FObs* obs, const float* pts_host, int64_t n, const D3F
                                      cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < HOST_STREAMS; ++i) D3F_CUDA(cudaStreamSynchronize(sc.st[i]));
+    return D3F_OK;
+}
+
+int d3f_eval_backward(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys, int32_t n_keys,
+                      const float* const* grad_out, const float* grad_dist, float* grad_pts,
+                      uint32_t flags, float mu, void* stream) {
+    if (!obs) return fail(D3F_EINVAL, "obs is NULL");
+    if (obs->V < 1 || obs->V > D3F_MAX_VIEWS) return fail(D3F_EINVAL, "V=%d outside 1..%d", obs->V, D3F_MAX_VIEWS);
+    if (!obs->pose || !obs->K || !obs->depth) return fail(D3F_EINVAL, "obs pose/K/depth pointer is NULL");
+    if (n < 0 || (n > 0 && (!pts || !grad_pts))) return fail(D3F_EINVAL, "backward: bad n / NULL pts or grad_pts");
+    if (!(mu > 0.f)) return fail(D3F_EINVAL, "mu=%g must be positive", (double)mu);
+    if (flags & ~D3F_FLAG_RECIP_NORM) return fail(D3F_EINVAL, "backward: unsupported flag bits 0x%x", flags);
+    if (n_keys < 0 || n_keys > D3F_MAX_KEYS || (n_keys > 0 && (!keys || !grad_out)))
+        return fail(D3F_EINVAL, "backward: bad keys / grad_out");
+    d3f::BwdKeySet ks;
+    memset(&ks, 0, sizeof(ks));
+    ks.n_keys = n_keys;
+    for (int k = 0; k < n_keys; ++k) {
+        if (!keys[k].data || (keys[k].dtype != D3F_F32 && keys[k].dtype != D3F_U8) || keys[k].h < 1 || keys[k].w < 1 || keys[k].C < 1)
+            return fail(D3F_EINVAL, "backward: keys[%d] invalid", k);
+        ks.data[k] = keys[k].data; ks.grad[k] = grad_out[k]; ks.dtype[k] = keys[k].dtype;
+        ks.h[k] = keys[k].h; ks.w[k] = keys[k].w; ks.C[k] = keys[k].C;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    if (n == 0) return D3F_OK;
+    d3f::EvalParams ep;
+    ep.pts = pts; ep.depth = obs->depth; ep.pose = obs->pose; ep.K = obs->K; ep.dist = nullptr; ep.valid = nullptr;
+    ep.n = n; ep.V = obs->V; ep.H = obs->H; ep.W = obs->W; ep.mu = mu; ep.flags = flags;
+    const int64_t blocks = (n + d3f::BWD_WARPS - 1) / d3f::BWD_WARPS;
+    if (blocks > 0x7fffffffll) return fail(D3F_EINVAL, "backward: n too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (flags & D3F_FLAG_RECIP_NORM)
+        d3f::field_backward_kernel<true><<<(unsigned)blocks, d3f::BWD_WARPS * 32, 0, st>>>(ep, ks, grad_dist, grad_pts);
+    else
+        d3f::field_backward_kernel<false><<<(unsigned)blocks, d3f::BWD_WARPS * 32, 0, st>>>(ep, ks, grad_dist, grad_pts);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    D3F_CUDA(cudaGetLastError());
     return D3F_OK;
 }
 

@@ -1,0 +1,149 @@
+// d3f_backward.cuh — gradient of the field query with respect to the query points.
+//
+// The reference's rigid_tracking (fusion.py:1608-1685) runs Adam through Fusion.eval with autograd:
+//   loss(feat(pts), dist(pts)) -> d loss / d pts.
+// What is differentiable in fusion.py:305-394 (everything else is a hard mask or a nearest-neighbour
+// lookup, whose gradient torch defines as zero):
+//   * the bilinear samples, through their pixel coordinates (grid_sample backward, align_corners=True,
+//     zero padding: out-of-range corners contribute nothing),
+//   * the distance weight exp(min(mu-|d|,0)/mu), through d = depth_nearest - z  (only where |d| > mu),
+//   * dist = sum_v clamp(d_v,-mu,mu) vis_v / (count+1e-6), through z (only where -mu <= d_v <= mu and at
+//     least one view sees the point: the 1e3 fill of fusion.py:367 is a constant),
+//   * pixel coordinates and z through the projection H_v [x y z 1]^T (the |z|<1e-4 patch makes the view
+//     invisible, so it carries no gradient).
+//
+// One warp per point (tracking evaluates a few hundred points; latency, not throughput, matters):
+// lanes 0..V-1 redo the per-view forward in parallel, then for every visible view and key the lanes
+// stride the channels and accumulate  sum_c g_c dr_c/dix,  sum_c g_c dr_c/diy,  sum_c g_c r_c,
+// reduced with a butterfly; lane 0 chains them to the camera frame and to the point.
+#pragma once
+#include "d3f_common.cuh"
+#include "d3f_generic.cuh"
+
+namespace d3f {
+
+constexpr int BWD_WARPS = 4;
+
+struct BwdKeySet {
+    const void* data[D3F_MAX_KEYS];
+    const float* grad[D3F_MAX_KEYS];     // (n,C) upstream gradient of the key's output, or nullptr
+    int32_t dtype[D3F_MAX_KEYS];
+    int32_t h[D3F_MAX_KEYS], w[D3F_MAX_KEYS], C[D3F_MAX_KEYS];
+    int32_t n_keys;
+};
+
+template <bool RECIP>
+__global__ void __launch_bounds__(BWD_WARPS * 32)
+field_backward_kernel(const EvalParams ep, const BwdKeySet ks, const float* __restrict__ grad_dist,
+                      float* __restrict__ grad_pts) {
+    __shared__ float sH[D3F_MAX_VIEWS * 12];
+    __shared__ float s_view[BWD_WARPS][D3F_MAX_VIEWS][8];   // px, py, cz, d, weight, vis, (unused x2)
+    const int V = ep.V;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = threadIdx.x; r < V * 3; r += BWD_WARPS * 32) {
+        const int v = r / 3, i = r - v * 3;
+        float row[4];
+        krt_row(ep.K + v * 9, ep.pose + v * 12, i, row);
+        sH[v * 12 + i * 4 + 0] = row[0]; sH[v * 12 + i * 4 + 1] = row[1];
+        sH[v * 12 + i * 4 + 2] = row[2]; sH[v * 12 + i * 4 + 3] = row[3];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * BWD_WARPS + warp;
+    if (i >= ep.n) return;
+    const float x = __ldg(ep.pts + i * 3), y = __ldg(ep.pts + i * 3 + 1), z = __ldg(ep.pts + i * 3 + 2);
+
+    // per-view forward, one lane per view
+    bool vis = false;
+    if (lane < V) {
+        float Hm[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) Hm[j] = sH[lane * 12 + j];
+        const ViewSample sm = view_sample<RECIP>(Hm, x, y, z, ep.depth + (size_t)lane * ep.H * ep.W, ep.H, ep.W, ep.mu, false);
+        vis = sm.vis;
+        float* sv = s_view[warp][lane];
+        sv[0] = sm.px; sv[1] = sm.py;
+        sv[2] = hdot(Hm + 8, x, y, z);           // camera z (a visible view never has the |z|<1e-4 patch)
+        sv[3] = sm.d; sv[4] = sm.weight; sv[5] = vis ? 1.f : 0.f;
+    }
+    const unsigned vis_mask = __ballot_sync(0xffffffffu, vis);
+    const float cnt = (float)__popc(vis_mask);
+    __syncwarp();
+    if (cnt == 0.f) {                            // no view sees the point: every output is a constant
+        if (lane < 3) grad_pts[i * 3 + lane] = 0.f;
+        return;
+    }
+    const float inv = __fdiv_rn(1.f, __fadd_rn(cnt, 1e-6f));
+    const float gd = grad_dist ? __ldg(grad_dist + i) : 0.f;
+
+    float gx = 0.f, gy = 0.f, gz = 0.f;          // accumulated by lane 0
+    for (int v = 0; v < V; ++v) {
+        if (!(vis_mask & (1u << v))) continue;
+        const float* sv = s_view[warp][v];
+        const float px = sv[0], py = sv[1], cz = sv[2], d = sv[3], weight = sv[4];
+        const float fac = weight * inv;
+        float G_px = 0.f, G_py = 0.f, G_w = 0.f;
+        for (int k = 0; k < ks.n_keys; ++k) {
+            if (!ks.grad[k]) continue;
+            const int h = ks.h[k], w = ks.w[k], C = ks.C[k];
+            // footprint with explicit in-range flags (a zero weight can also be a cell-border weight)
+            const float ix = to_map_index<RECIP>(px, ep.W, w), iy = to_map_index<RECIP>(py, ep.H, h);
+            const float x0 = floorf(ix), y0 = floorf(iy);
+            const float wx = ix - x0, wy = iy - y0;
+            const float x1 = x0 + 1.f, y1 = y0 + 1.f, xm = (float)(w - 1), ym = (float)(h - 1);
+            const bool x0ok = x0 >= 0.f && x0 <= xm, x1ok = x1 >= 0.f && x1 <= xm;
+            const bool y0ok = y0 >= 0.f && y0 <= ym, y1ok = y1 >= 0.f && y1 <= ym;
+            const int x0c = (int)fminf(fmaxf(x0, 0.f), xm), x1c = (int)fminf(fmaxf(x1, 0.f), xm);
+            const int y0c = (int)fminf(fmaxf(y0, 0.f), ym), y1c = (int)fminf(fmaxf(y1, 0.f), ym);
+            const float m00 = (x0ok && y0ok) ? 1.f : 0.f, m01 = (x1ok && y0ok) ? 1.f : 0.f;
+            const float m10 = (x0ok && y1ok) ? 1.f : 0.f, m11 = (x1ok && y1ok) ? 1.f : 0.f;
+            const size_t vbase = (size_t)v * h * w;
+            const size_t o00 = (vbase + (size_t)y0c * w + x0c) * C, o01 = (vbase + (size_t)y0c * w + x1c) * C;
+            const size_t o10 = (vbase + (size_t)y1c * w + x0c) * C, o11 = (vbase + (size_t)y1c * w + x1c) * C;
+            const float* g = ks.grad[k] + (size_t)i * C;
+            float s_ix = 0.f, s_iy = 0.f, s_r = 0.f;
+            for (int c = lane; c < C; c += 32) {
+                float f00, f01, f10, f11;
+                if (ks.dtype[k] == D3F_F32) {
+                    const float* vol = static_cast<const float*>(ks.data[k]);
+                    f00 = __ldg(vol + o00 + c); f01 = __ldg(vol + o01 + c); f10 = __ldg(vol + o10 + c); f11 = __ldg(vol + o11 + c);
+                } else {
+                    const uint8_t* vol = static_cast<const uint8_t*>(ks.data[k]);
+                    f00 = (float)__ldg(vol + o00 + c); f01 = (float)__ldg(vol + o01 + c);
+                    f10 = (float)__ldg(vol + o10 + c); f11 = (float)__ldg(vol + o11 + c);
+                }
+                f00 *= m00; f01 *= m01; f10 *= m10; f11 *= m11;
+                const float gc = __ldg(g + c);
+                s_ix = fmaf(gc, (f01 - f00) * (1.f - wy) + (f11 - f10) * wy, s_ix);
+                s_iy = fmaf(gc, (f10 - f00) * (1.f - wx) + (f11 - f01) * wx, s_iy);
+                s_r = fmaf(gc, (f00 * (1.f - wx) + f01 * wx) * (1.f - wy) + (f10 * (1.f - wx) + f11 * wx) * wy, s_r);
+            }
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) {
+                s_ix += __shfl_xor_sync(0xffffffffu, s_ix, sh);
+                s_iy += __shfl_xor_sync(0xffffffffu, s_iy, sh);
+                s_r += __shfl_xor_sync(0xffffffffu, s_r, sh);
+            }
+            // d ix / d px = (w-1)/(W-1): x_norm = px/(W-1)*2-1, ix = (x_norm+1)*(w-1)/2
+            G_px += fac * s_ix * ((float)(w - 1) / (float)(ep.W - 1));
+            G_py += fac * s_iy * ((float)(h - 1) / (float)(ep.H - 1));
+            G_w += inv * s_r;
+        }
+        // weight = exp(min(mu-|d|,0)/mu): d weight / d d = -sign(d) weight / mu where |d| >= mu (torch's clamp passes
+        // the gradient at equality), else 0
+        float G_d = (fabsf(d) >= ep.mu) ? G_w * weight * (d > 0.f ? -1.f : 1.f) / ep.mu : 0.f;
+        // dist term: clamp passes the gradient where -mu <= d <= mu
+        if (d >= -ep.mu && d <= ep.mu) G_d += gd * inv;
+        // d = depth_nearest - cz ; px = cx/cz ; py = cy/cz
+        const float G_cx = G_px / cz, G_cy = G_py / cz;
+        const float G_cz = -G_d - (G_px * px + G_py * py) / cz;
+        const float* Hm = sH + v * 12;
+        gx += Hm[0] * G_cx + Hm[4] * G_cy + Hm[8] * G_cz;
+        gy += Hm[1] * G_cx + Hm[5] * G_cy + Hm[9] * G_cz;
+        gz += Hm[2] * G_cx + Hm[6] * G_cy + Hm[10] * G_cz;
+    }
+    if (lane == 0) {
+        grad_pts[i * 3 + 0] = gx; grad_pts[i * 3 + 1] = gy; grad_pts[i * 3 + 2] = gz;
+    }
+}
+
+}  // namespace d3f

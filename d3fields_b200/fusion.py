@@ -46,6 +46,47 @@ def create_init_grid(boundaries, step_size):
     return torch.stack([gx, gy, gz], dim=-1).reshape(-1, 3), gx.shape
 
 
+class _FieldQuery(torch.autograd.Function):
+    """Fusion.eval as a differentiable function of the query points (the reference gets this from torch autograd;
+    its rigid_tracking optimises an SE(3) pose through eval, fusion.py:1643-1665).  Backward is one launch of
+    d3f_eval_backward; the observation is a constant."""
+
+    @staticmethod
+    def forward(ctx, pts, fusion, names):
+        res = fusion._run(pts.detach(), names, False, False)
+        ctx.fusion, ctx.names = fusion, tuple(names)
+        ctx.obs = {k: fusion.curr_obs_torch[k] for k in ('pose', 'K', 'depth') + tuple(names)}   # what forward saw
+        ctx.mu, ctx.flags = float(fusion.mu), fusion._flags(False)
+        ctx.save_for_backward(pts.detach())
+        ctx.mark_non_differentiable(res['valid_mask'])
+        return (res['dist'], res['valid_mask']) + tuple(res[k] for k in names)
+
+    @staticmethod
+    def backward(ctx, g_dist, _g_valid, *g_feats):
+        (pts,) = ctx.saved_tensors
+        pts = pts.contiguous()
+        o = ctx.obs
+        depth = o['depth']
+        V, H, W = (int(x) for x in depth.shape)
+        dev = depth.device
+        keys, grads = [], []
+        for name, g in zip(ctx.names, g_feats):
+            vol = o[name]
+            if vol.dtype == torch.bool:
+                vol = vol.view(torch.uint8)
+            dt = _native.D3F_F32 if vol.dtype == torch.float32 else _native.D3F_U8
+            keys.append((vol.data_ptr(), dt, int(vol.shape[1]), int(vol.shape[2]), int(vol.shape[3])))
+            grads.append(None if g is None else g.contiguous().float())
+        gd = None if g_dist is None else g_dist.contiguous().float()
+        grad_pts = torch.empty_like(pts)
+        with torch.cuda.device(dev):
+            _native.eval_backward(V, H, W, o['pose'].data_ptr(), o['K'].data_ptr(), depth.data_ptr(), pts.data_ptr(),
+                                  int(pts.shape[0]), keys, [None if g is None else g.data_ptr() for g in grads],
+                                  None if gd is None else gd.data_ptr(), grad_pts.data_ptr(), ctx.flags, ctx.mu,
+                                  torch.cuda.current_stream(dev).cuda_stream)
+        return grad_pts, None, None
+
+
 def _as_device(t, device, dtype=None):
     if isinstance(t, np.ndarray):
         t = torch.from_numpy(t)
@@ -253,6 +294,15 @@ class Fusion:
         tensors for 'dist' / 'valid_mask' / any name; the kernel writes them in place."""
         if isinstance(pts, torch.Tensor) and not pts.is_cuda and return_inter:
             raise ValueError('return_inter needs device points')
+        if isinstance(pts, torch.Tensor) and pts.requires_grad and torch.is_grad_enabled():
+            if not pts.is_cuda or return_inter or out is not None:
+                raise ValueError('differentiable eval needs device points, return_inter=False and no out=')
+            self._check_pts(pts)
+            names = list(return_names)
+            outs = _FieldQuery.apply(pts, self, names)
+            res = {'dist': outs[0], 'valid_mask': outs[1]}
+            res.update({k: outs[2 + i] for i, k in enumerate(names)})
+            return res
         return self._run(pts, return_names, return_inter, eval_dist=False, out=out)
 
     def eval_dist(self, pts):

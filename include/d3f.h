@@ -106,6 +106,19 @@ int d3f_eval_host(const D3FObs* obs, const float* pts_host, int64_t n,
                   float* const* out_host,
                   uint32_t flags, float mu);
 
+/* Gradient of d3f_eval's outputs with respect to the query points: what torch autograd computes when the
+ * reference's rigid_tracking back-propagates through Fusion.eval (reference fusion.py:1643-1665).
+ *   grad_out[k]  (n,C_k) upstream gradient of out[k], or NULL for a key that does not need one
+ *   grad_dist    (n) upstream gradient of dist, or NULL
+ *   grad_pts     (n,3) out
+ * Differentiable terms: the bilinear samples through their pixel coordinates, the distance weight and the
+ * clamped dist through the camera-frame depth; visibility masks, nearest-depth lookups and the 1e3 fill are
+ * constants, exactly as in torch.  D3F_FLAG_EVAL_DIST is not supported. */
+int d3f_eval_backward(const D3FObs* obs, const float* pts, int64_t n,
+                      const D3FKey* keys, int32_t n_keys,
+                      const float* const* grad_out, const float* grad_dist,
+                      float* grad_pts, uint32_t flags, float mu, void* stream);
+
 /* Fused PCA projection of a descriptor field: y = (x - mean) @ components^T, the
  * sklearn.decomposition.PCA.transform the reference applies on the host to eval's
  * 'dino_feats' (reference fusion.py:1386-1392, weights from pca_model/*.pkl).

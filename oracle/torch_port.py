@@ -44,10 +44,10 @@ def _sample(maps_nchw, pix, H, W, mode):
     return s.squeeze(2).permute(0, 2, 1)
 
 
-@torch.no_grad()
 def eval_chunk(obs: Dict[str, torch.Tensor], H: int, W: int, pts: torch.Tensor,
                return_names: Iterable[str] = (), mu: float = 0.02) -> Dict[str, torch.Tensor]:
-    """reference fusion.py:305-394 on one chunk"""
+    """reference fusion.py:305-394 on one chunk.  Differentiable with respect to pts exactly like the reference
+    (rigid_tracking back-propagates through it, fusion.py:1650-1665); wrap in torch.no_grad() for timing."""
     pix, in_front, z = _project(pts, obs['pose'], obs['K'])
     z = z[..., 0]
     seen_depth = _sample(obs['depth'].unsqueeze(1), pix, H, W, 'nearest')[..., 0]

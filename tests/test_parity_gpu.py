@@ -318,3 +318,53 @@ def test_pca_field_via_projected_volume(C, k):
     # plain projection kernel without centring
     z = f.pca_project(ref['dino_feats'], None, comp).cpu().numpy()
     assert np.abs(z - x @ comp.T.astype(np.float64)).max() <= 1e-4 * max(1e-6, np.abs(x @ comp.T).max())
+
+
+def test_backward_matches_torch_autograd_through_the_reference_operator_sequence():
+    """d loss / d pts through Fusion.eval (d3f_eval_backward) against torch autograd through oracle/torch_port.py —
+    the reference's own operator sequence, which is what its rigid_tracking differentiates (fusion.py:1650-1665).
+    Points sit within a few mu of the surfaces so every differentiable term is active: bilinear coordinates,
+    the distance weight (|d| > mu), the clamped dist (|d| < mu)."""
+    from oracle import torch_port as TP
+    sc = S.make_scene(4, 240, 320, seed=51, feat=(24, 32, 64), num_inst=4)
+    rs = np.random.RandomState(51)
+    base = S.grid_points(60, 60, 40)
+    ref0 = O.field_eval(base, sc.pose, sc.K, sc.depth, sc.H, sc.W)
+    near = base[np.abs(ref0['dist']) < 0.0199][::7][:1500]           # inside the truncation band
+    pts_np = np.concatenate([near, near + rs.normal(0, 0.03, near.shape).astype(np.float32), S.scattered_points(500, 51)])
+    n = len(pts_np)
+    Gf = rs.standard_normal((n, 64)).astype(np.float32)
+    Gm = rs.standard_normal((n, 4)).astype(np.float32)
+    gd = rs.standard_normal(n).astype(np.float32)
+    # reference operators, CPU float32 autograd
+    obs = TP.obs_from_scene(sc)
+    p_ref = torch.from_numpy(pts_np).clone().requires_grad_(True)
+    o = TP.eval_chunk(obs, sc.H, sc.W, p_ref, ['dino_feats', 'mask'])
+    loss = (o['dino_feats'] * torch.from_numpy(Gf)).sum() + (o['mask'] * torch.from_numpy(Gm)).sum() + (o['dist'] * torch.from_numpy(gd)).sum()
+    loss.backward()
+    g_ref = p_ref.grad.numpy()
+    # native
+    f = make_fusion(sc, DEV)
+    p = torch.from_numpy(pts_np).to(DEV).requires_grad_(True)
+    out = f.eval(p, return_names=['dino_feats', 'mask'])
+    assert out['dino_feats'].requires_grad and out['dist'].requires_grad and not out['valid_mask'].requires_grad
+    loss2 = (out['dino_feats'] * torch.from_numpy(Gf).to(DEV)).sum() + (out['mask'] * torch.from_numpy(Gm).to(DEV)).sum() \
+        + (out['dist'] * torch.from_numpy(gd).to(DEV)).sum()
+    loss2.backward()
+    g = p.grad.cpu().numpy()
+    assert np.isfinite(g).all()
+    scale = np.abs(g_ref).max()
+    assert scale > 1.0
+    err = np.abs(g - g_ref)
+    assert (err <= 2e-3 * np.abs(g_ref) + 2e-4 * scale).all(), f'max err {err.max():.3e} at scale {scale:.3e}'
+    assert (np.abs(g_ref).max(1) > 0).mean() > 0.3           # the case has plenty of points with gradient
+    # points no view sees get exactly zero
+    none = ~out['valid_mask'].cpu().numpy()
+    assert none.any() and (g[none] == 0).all() and (g_ref[none] == 0).all()
+    # dist-only gradient (return_names=[])
+    p2 = torch.from_numpy(pts_np).to(DEV).requires_grad_(True)
+    (f.eval(p2, return_names=[])['dist'] * torch.from_numpy(gd).to(DEV)).sum().backward()
+    p3 = torch.from_numpy(pts_np).clone().requires_grad_(True)
+    (TP.eval_chunk(obs, sc.H, sc.W, p3, [])['dist'] * torch.from_numpy(gd)).sum().backward()
+    e2 = np.abs(p2.grad.cpu().numpy() - p3.grad.numpy())
+    assert (e2 <= 2e-3 * np.abs(p3.grad.numpy()) + 2e-4 * np.abs(p3.grad.numpy()).max()).all()
