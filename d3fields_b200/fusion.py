@@ -87,6 +87,25 @@ class _FieldQuery(torch.autograd.Function):
         return grad_pts, None, None
 
 
+def create_init_grid_device(boundaries, step_size, device='cuda:0'):
+    """create_init_grid (reference fusion.py:79-88) generated on the device by d3f_create_grid: the 101 M-point sweep
+    of select_features_rand (fusion.py:1420-1424) then never exists on the host nor crosses PCIe.  Same point count
+    and order as create_init_grid; coordinates are float(lower + step*i) + float(step/2), which can differ from
+    torch.arange's vectorised CPU values by one ulp."""
+    import math
+    dev = torch.device(device)
+    dims = []
+    for a in ('x', 'y', 'z'):
+        lo, hi = float(boundaries[a + '_lower']), float(boundaries[a + '_upper'])
+        dims.append(max(int(math.ceil((hi - lo) / float(step_size))), 0))
+    nx, ny, nz = dims
+    pts = torch.empty((nx * ny * nz, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _native.create_grid(float(boundaries['x_lower']), float(boundaries['y_lower']), float(boundaries['z_lower']),
+                            float(step_size), nx, ny, nz, pts.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    return pts, torch.Size(dims)
+
+
 def _as_device(t, device, dtype=None):
     if isinstance(t, np.ndarray):
         t = torch.from_numpy(t)
