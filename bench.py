@@ -231,24 +231,41 @@ def main():
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
+    side = torch.cuda.Stream(dev) if world > 1 else None
+
     def step():
         if world == 1:
             return f.eval(pts, return_names=names)
-        out = f.eval(pts, return_names=names, out=slot)
-        dist.all_gather_into_tensor(g_pack.view(-1), g_pack[rank])              # one in-place collective for both fields
+        # N > 1: the compact fields and their collective run on a side stream — the light dist/valid kernel writes this
+        # rank's slot, one in-place all_gather follows — while the descriptor kernel runs on the main stream; the
+        # step ends when both have finished.
+        main = torch.cuda.current_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            f.eval(pts, return_names=[], out=slot)
+            dist.all_gather_into_tensor(g_pack.view(-1), g_pack[rank])
+        out = f.eval(pts, return_names=names)
+        main.wait_stream(side)
         return out
 
+    clk = ClockSampler(local)
+    clk.__enter__()                    # samples cover the warm-up and the timed region (the latter lasts ~20 ms)
+    t_load0 = time.perf_counter()
     for _ in range(args.warmup):
         out = step()
         flush.zero_()
     torch.cuda.synchronize(dev)
+    while time.perf_counter() - t_load0 < 0.6:      # keep the GPU under this load until nvidia-smi has sampled it
+        out = step()
+        flush.zero_()
+        torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = _native.launch_count()
     torch.cuda.synchronize(dev)
-    with ClockSampler(local) as clk:
+    if True:
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             starts[i].record()
@@ -259,6 +276,7 @@ def main():
         if world > 1:
             dist.barrier()
         t_wall = time.perf_counter() - t_wall0
+    clk.__exit__(None, None, None)
     launches = _native.launch_count() - launches0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(sum(step_ms))
@@ -322,7 +340,7 @@ def main():
         'config': {'workload': f'cfg2a: {n} grid points per GPU (z fastest), V={V} views {H}x{W}, dino_feats '
                                f'({h},{w},{C}) f32 per view, return_names=[dino_feats]' + (' [scattered]' if args.scattered else ''),
                    'points_per_gpu': n, 'global_points': world * n, 'sharding': f'x-slabs over {world} ranks',
-                   'collective': 'one in-place all_gather of the packed (dist f32 | valid_mask u8) slots, 5 B/point, in the timed step' if world > 1 else 'none',
+                   'collective': 'one in-place all_gather of the packed (dist f32 | valid_mask u8) slots, 5 B/point, on a side stream overlapping the descriptor kernel, joined inside the timed step' if world > 1 else 'none',
                    'l2': 'outputs 4.1 GB per step exceed L2; plus a 256 MiB flush between timed steps (not timed)',
                    'timing': 'CUDA events per step on the launching stream, summed; max over ranks'},
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),

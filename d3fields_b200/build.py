@@ -60,17 +60,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_current():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-I', INCLUDE, '-o', LIB_PATH, os.path.join(CSRC, 'd3f_abi.cu')]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
-    with open(os.path.join(LIB_DIR, 'build.log'), 'w') as fh:
-        fh.write(' '.join(cmd) + '\n' + log)
-    if proc.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + log)
-    if verbose:
-        print(log)
-    with open(STAMP, 'w') as fh:
-        fh.write(source_hash())
+    import fcntl
+    with open(os.path.join(LIB_DIR, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)          # several ranks may import the package at once
+        try:
+            if not force and is_current():        # another process built it while we waited
+                return LIB_PATH
+            tmp = LIB_PATH + f'.tmp{os.getpid()}'
+            cmd = [_nvcc()] + NVCC_FLAGS + ['-I', INCLUDE, '-o', tmp, os.path.join(CSRC, 'd3f_abi.cu')]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            log = proc.stdout + proc.stderr
+            with open(os.path.join(LIB_DIR, 'build.log'), 'w') as fh:
+                fh.write(' '.join(cmd) + '\n' + log)
+            if proc.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError('nvcc failed:\n' + log)
+            os.replace(tmp, LIB_PATH)             # atomic: a reader never sees a half-written library
+            if verbose:
+                print(log)
+            with open(STAMP, 'w') as fh:
+                fh.write(source_hash())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
