@@ -393,3 +393,43 @@ def test_cuda_rounding_mode_against_the_reference_operators_run_by_torch_on_the_
     print('mismatch vs torch-CUDA reference ops  (valid_mask frac, dist>1e-6 frac, max feat err):', res)
     assert res['cuda'][0] <= 2e-4 and res['cpu'][0] <= 2e-3
     assert res['cuda'][1] <= 2e-3
+
+
+def test_pose_recovery_by_gradient_descent_through_eval():
+    """The use the backward exists for (reference rigid_tracking, fusion.py:1608-1685): points on the sphere are moved
+    by a small unknown translation; Adam on the translation, through Fusion.eval's descriptors and dist, brings them
+    back.  A smooth low-frequency feature volume makes the descriptor loss informative."""
+    V, H, W = 4, 240, 320
+    sc = S.make_scene(V, H, W, seed=71, hole_frac=0.0)
+    hh, ww, C = 24, 32, 128
+    yy, xx = np.meshgrid(np.linspace(0, 1, hh), np.linspace(0, 1, ww), indexing='ij')
+    rs = np.random.RandomState(71)
+    fr = rs.uniform(0.5, 2.0, size=(C, 2)); ph = rs.uniform(0, 6.28, size=C)
+    vol = np.sin(2 * np.pi * (fr[:, 0] * xx[..., None] + fr[:, 1] * yy[..., None]) + ph).astype(np.float32)   # (h,w,C)
+    sc.maps['dino_feats'] = np.ascontiguousarray(np.broadcast_to(vol, (V, hh, ww, C))).copy()
+    f = make_fusion(sc, DEV)
+    # surface points: upper hemisphere of the r=0.25 sphere
+    u = rs.uniform(0, 2 * np.pi, 400); cz = rs.uniform(0.3, 0.95, 400)
+    src = (0.25 * np.stack([np.sqrt(1 - cz ** 2) * np.cos(u), np.sqrt(1 - cz ** 2) * np.sin(u), cz], -1)).astype(np.float32)
+    src_t = torch.from_numpy(src).to(DEV)
+    with torch.no_grad():
+        target = f.eval(src_t, return_names=['dino_feats'])
+    keep = target['valid_mask']
+    assert keep.float().mean() > 0.8
+    src_t, tfeat = src_t[keep], target['dino_feats'][keep]
+    true_shift = torch.tensor([0.012, -0.009, 0.006], device=DEV)
+    moved = src_t + true_shift
+    t = torch.zeros(3, device=DEV, requires_grad=True)
+    opt = torch.optim.Adam([t], lr=2e-3)
+    first = None
+    for it in range(150):
+        opt.zero_grad()
+        out = f.eval(moved - t, return_names=['dino_feats'])
+        w = out['valid_mask'].float().unsqueeze(-1)
+        loss = (((out['dino_feats'] - tfeat) ** 2) * w).sum() / w.sum() / C + 10.0 * (out['dist'].clamp(-0.02, 0.02) ** 2).mean()
+        loss.backward()
+        opt.step()
+        first = loss.item() if first is None else first
+    err0 = true_shift.norm().item()
+    err = (t.detach() - true_shift).norm().item()
+    assert loss.item() < 0.2 * first and err < 0.35 * err0, (first, loss.item(), err0, err)

@@ -107,6 +107,22 @@ def main():
         rec('dist_only_1m', 1_000_000, ms, mn, [])
         ms, mn = timed(lambda: f.eval(grid16m, []), flush=flush)
         rec('dist_only_16m', 16_000_000, ms, mn, [])
+    if want('sweep_101m'):
+        # select_features_rand's sweep (reference fusion.py:1420-1428): 800x700x181 grid at 1 mm, batch_eval(grid, ['mask'])
+        from d3fields_b200 import create_init_grid_device
+        b = dict(x_lower=-0.4, x_upper=0.4, y_lower=-0.4, y_upper=0.3, z_lower=-0.2, z_upper=-0.019)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        big, shape = create_init_grid_device(b, 0.001, DEV)
+        torch.cuda.synchronize(); t_grid = time.perf_counter() - t0
+        nbig = big.shape[0]
+        ms, mn = timed(lambda: f.eval(big, ['mask_u8']), warm=1, reps=3)
+        r = dict(name='sweep_101m_grid_mask_u8', n=nbig, ms=ms, ms_min=mn, mpts_s=nbig / ms / 1e3, variant=_native.last_variant(0),
+                 note=f'grid {tuple(shape)} generated on device in {t_grid * 1e3:.1f} ms; reference: 1690 chunks of 60 000')
+        results.append(r); print(json.dumps(r), flush=True)
+        ms, mn = timed(lambda: f.eval(big, []), warm=1, reps=3)
+        r = dict(name='sweep_101m_grid_dist_only', n=nbig, ms=ms, ms_min=mn, mpts_s=nbig / ms / 1e3, variant=_native.last_variant(0), note='')
+        results.append(r); print(json.dumps(r), flush=True)
+        del big
     if want('multi_key'):
         ms, mn = timed(lambda: f.eval(grid1m, ['dino_feats', 'mask', 'color_tensor']), flush=flush)
         rec('vis_repr_3keys', 1_000_000, ms, mn, [(48, 64, 1024, 4), (480, 640, 8, 4), (480, 640, 3, 4)],
