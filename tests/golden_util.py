@@ -16,15 +16,17 @@ def _sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def _points(meta, blob):
+def _points(meta, blob, scene):
+    """Rebuild the query points of a fixture from its 'pts_how' recipe (see oracle/gen_golden.py cases())."""
     how = meta['pts_how']
     if 'in.pts' in blob:
         return blob['in.pts']
     if how == 'config_points:cfg1':
         return S.config_points('cfg1')
-    if how.startswith('grid30+'):
-        sc = S.make_scene(4, 480, 640, seed=1)
-        return np.concatenate([S.grid_points(30, 30, 30), S.scattered_points(12000, 1), S.adversarial_points(sc, 3)])
+    if how == 'grid30+scattered12000(seed1)+adversarial(seed3)':
+        return np.concatenate([S.grid_points(30, 30, 30), S.scattered_points(12000, 1), S.adversarial_points(scene, 3)])
+    if how == 'grid17x13x11+scattered3001(seed2)+adversarial(seed5,16)':
+        return np.concatenate([S.grid_points(17, 13, 11), S.scattered_points(3001, 2), S.adversarial_points(scene, 5, 16)])
     if how == 'grid52x50x50':
         return S.grid_points(52, 50, 50)
     raise KeyError(how)
@@ -43,14 +45,7 @@ class Golden:
             self.scene = S.make_scene(mk['V'], mk['H'], mk['W'], seed=mk['seed'],
                                       feat=tuple(mk['feat']) if mk['feat'] else None,
                                       num_inst=mk['num_inst'], color=mk['color'])
-        if 'in.pts' in blob:
-            self.pts = blob['in.pts']
-        elif name == 'odd3v':
-            self.pts = np.concatenate([S.grid_points(17, 13, 11), S.scattered_points(3001, 2),
-                                       S.adversarial_points(self.scene, 5, 16)])
-        else:
-            self.pts = _points(self.meta, blob)
-        self.pts = np.ascontiguousarray(self.pts, dtype=np.float32)
+        self.pts = np.ascontiguousarray(_points(self.meta, blob, self.scene), dtype=np.float32)
         self.rows = blob['rows']
         self.names = self.meta['names']
         self.mu = self.meta['mu']
