@@ -42,6 +42,25 @@ def broadcast_observation(obs: Dict[str, object], src: int = 0, group=None) -> N
             dist.broadcast(v, src=src, group=group)
 
 
+def block_interleaved_index(n: int, rank: int, world: int, block: int) -> torch.Tensor:
+    """Indices of rank `rank` when blocks of `block` consecutive points (e.g. one x-plane of a grid, ny*nz points) are
+    dealt round-robin to the ranks.  Use it when the scene is spatially heterogeneous: contiguous slabs then differ in
+    work (the cost of a point depends on how many views see it) and the step is the max over ranks; interleaved shares
+    are statistically identical.  Requires n % (block*world) == 0."""
+    if block <= 0 or n % (block * world) != 0:
+        raise ValueError(f'n={n} must be a multiple of block*world={block * world}')
+    blocks = torch.arange(rank, n // block, world)
+    return (blocks[:, None] * block + torch.arange(block)[None, :]).reshape(-1)
+
+
+def deinterleave(gathered: torch.Tensor, world: int, block: int) -> torch.Tensor:
+    """Rank-major all-gather result of block-interleaved shares -> canonical point order."""
+    n = gathered.shape[0]
+    per = n // world
+    g = gathered.reshape(world, per // block, block, *gathered.shape[1:])
+    return g.transpose(0, 1).reshape(n, *gathered.shape[1:])
+
+
 def eval_sharded(eval_fn: Callable[..., Dict[str, torch.Tensor]], pts: torch.Tensor,
                  return_names: Iterable[str] = (), gather: Sequence[str] = ('dist', 'valid_mask'),
                  channels: Optional[Dict[str, int]] = None, group=None) -> Dict[str, object]:

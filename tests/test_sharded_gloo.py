@@ -11,7 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from d3fields_b200 import scene as S
-from d3fields_b200.sharded import broadcast_observation, eval_sharded, shard_range, slab_capacity
+from d3fields_b200.sharded import (block_interleaved_index, broadcast_observation, deinterleave, eval_sharded,
+                                   shard_range, slab_capacity)
 
 
 def test_shard_ranges_tile_the_points():
@@ -80,3 +81,18 @@ def test_sharded_eval_over_gloo(world, n):
         assert p.exitcode == 0, f'worker exit code {p.exitcode}'
     res = dict(q.get(timeout=5) for _ in range(world))
     assert res == {r: True for r in range(world)}
+
+
+def test_block_interleaved_shares_and_deinterleave():
+    n, world, block = 2 * 3 * 5 * 4, 3, 5
+    idx = [block_interleaved_index(n, r, world, block) for r in range(world)]
+    allidx = torch.cat(idx)
+    assert sorted(allidx.tolist()) == list(range(n))                 # a partition
+    assert idx[1][:block].tolist() == list(range(block, 2 * block))  # rank 1 starts with block 1
+    field = torch.arange(n, dtype=torch.float32) * 10
+    gathered = torch.cat([field[i] for i in idx])                    # what a rank-major all_gather returns
+    assert torch.equal(deinterleave(gathered, world, block), field)
+    f2 = torch.stack([field, -field], 1)
+    assert torch.equal(deinterleave(torch.cat([f2[i] for i in idx]), world, block), f2)
+    with pytest.raises(ValueError):
+        block_interleaved_index(n + 1, 0, world, block)
