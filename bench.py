@@ -212,8 +212,13 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        import datetime
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        # The only collective here is a 5 B/point all-gather: NVLink-SHARP multicast buys nothing for it, and its setup
+        # is the slowest and most fragile part of communicator creation when jobs of different rank counts follow each
+        # other on one box.  A bounded timeout turns any rendezvous problem into an error instead of a hang.
+        os.environ.setdefault('NCCL_NVLS_ENABLE', '0')
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     n = args.points_per_gpu
     V, H, W = CFG['V'], CFG['H'], CFG['W']
@@ -253,15 +258,16 @@ def main():
 
     clk = ClockSampler(local)
     clk.__enter__()                    # samples cover the warm-up and the timed region (the latter lasts ~20 ms)
-    t_load0 = time.perf_counter()
     for _ in range(args.warmup):
         out = step()
         flush.zero_()
     torch.cuda.synchronize(dev)
-    while time.perf_counter() - t_load0 < 0.6:      # keep the GPU under this load until nvidia-smi has sampled it
+    # Keep the GPU under this load for ~0.5 s so nvidia-smi samples it.  The count is FIXED, never time-based: every
+    # step contains a collective at N > 1, so all ranks must run exactly the same number of steps.
+    for _ in range(500):
         out = step()
         flush.zero_()
-        torch.cuda.synchronize(dev)
+    torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
