@@ -103,6 +103,19 @@ def cases():
     sc = S.make_scene(4, 240, 320, seed=4, feat=(24, 32, 16), num_inst=4)
     out['batch3chunks'] = dict(scene=sc, make=mk, pts=S.grid_points(52, 50, 50), pts_how='grid52x50x50',
                                names=['dino_feats', 'mask'], mu=0.02, batch=True)
+    # ---- CPU-only extras (tests/test_oracle_golden.py::EXTRA_CASES): more pinning of the restatements -------------
+    mk = dict(V=1, H=64, W=80, seed=6, feat=[6, 8, 1024], num_inst=0, color=False)
+    sc = S.make_scene(1, 64, 80, seed=6, feat=(6, 8, 1024))
+    out['x_v1_c1024'] = dict(scene=sc, make=mk, pts=np.concatenate([S.grid_points(12, 12, 8), S.scattered_points(800, 6)]),
+                             pts_how='grid12x12x8+scattered800(seed6)', names=['dino_feats'], mu=0.02)
+    mk = dict(V=2, H=48, W=64, seed=7, feat=[48, 64, 4], num_inst=2, color=True)
+    sc = S.make_scene(2, 48, 64, seed=7, feat=(48, 64, 4), num_inst=2, color=True)
+    out['x_fullres_tinymu'] = dict(scene=sc, make=mk, pts=np.concatenate([S.grid_points(20, 20, 20), S.adversarial_points(sc, 7, 32)]),
+                                   pts_how='grid20^3+adversarial(seed7,32)', names=['dino_feats', 'mask', 'color_tensor'], mu=0.002)
+    mk = dict(V=5, H=90, W=120, seed=8, feat=[9, 12, 6], num_inst=0, color=False)
+    sc = S.make_scene(5, 90, 120, seed=8, feat=(9, 12, 6))
+    out['x_v5_far'] = dict(scene=sc, make=mk, pts=(S.scattered_points(6000, 8, sigma=1.5)), pts_how='scattered6000(seed8,sigma1.5)',
+                           names=['dino_feats'], mu=0.1)
     return out
 
 

@@ -9,7 +9,8 @@ import numpy as np
 from d3fields_b200 import scene as S
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['cfg1', 'mixed4v', 'odd3v', 'ties', 'batch3chunks']
+CASES = ['cfg1', 'mixed4v', 'odd3v', 'ties', 'batch3chunks']          # checked on CPU (oracles) and on the GPU
+EXTRA_CASES = ['x_v1_c1024', 'x_fullres_tinymu', 'x_v5_far']            # CPU only: extra pinning of the oracles
 
 
 def _sha(a):
@@ -29,6 +30,12 @@ def _points(meta, blob, scene):
         return np.concatenate([S.grid_points(17, 13, 11), S.scattered_points(3001, 2), S.adversarial_points(scene, 5, 16)])
     if how == 'grid52x50x50':
         return S.grid_points(52, 50, 50)
+    if how == 'grid12x12x8+scattered800(seed6)':
+        return np.concatenate([S.grid_points(12, 12, 8), S.scattered_points(800, 6)])
+    if how == 'grid20^3+adversarial(seed7,32)':
+        return np.concatenate([S.grid_points(20, 20, 20), S.adversarial_points(scene, 7, 32)])
+    if how == 'scattered6000(seed8,sigma1.5)':
+        return S.scattered_points(6000, 8, sigma=1.5)
     raise KeyError(how)
 
 
@@ -68,6 +75,13 @@ class Golden:
         got = a if full else a[self.rows]
         if a.dtype == np.float32:
             nbad = int((got.view(np.uint32) != stored.view(np.uint32)).sum())
+            if self.meta['V'] >= 5:
+                # torch's CPU sum over the view axis is sequential for V <= 4 (every case the reference runs: 4 cameras)
+                # but uses a 4-accumulator cascade on the tail elements of each vectorised chunk for V >= 5, in a way
+                # that depends on the machine's vector width: there the reference's own dist is defined to 1 ulp only.
+                ulp = np.abs(got.view(np.int32).astype(np.int64) - stored.view(np.int32).astype(np.int64))
+                if int(ulp.max()) <= 2:
+                    return
         else:
             nbad = int((got != stored).sum())
         raise AssertionError(f'{key}: sha256 differs from the reference; {nbad} mismatches among the '

@@ -4,11 +4,11 @@ GPU box is then compared with the oracle and with the same fixtures."""
 import numpy as np
 import pytest
 
-from golden_util import CASES, Golden
+from golden_util import CASES, EXTRA_CASES, Golden
 from oracle import field_oracle as O
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES + EXTRA_CASES)
 def test_numpy_oracle_matches_reference_golden(name):
     g = Golden(name)
     sc = g.scene
@@ -45,7 +45,7 @@ def test_uint8_mask_is_read_as_its_float_value():
     assert np.array_equal(a['mask'], b['mask'])
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES + EXTRA_CASES)
 def test_torch_port_matches_reference_golden(name):
     """oracle/torch_port.py (the CPU-baseline stand-in for the reference) gives the reference's results."""
     import torch
@@ -61,7 +61,7 @@ def test_torch_port_matches_reference_golden(name):
         g.check_close(k, out[k].numpy())
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES + EXTRA_CASES)
 def test_c_oracle_matches_reference_golden_and_numpy_oracle(name):
     """oracle/d3f_oracle.c: pinned against the reference's golden vectors, and equal to the numpy
     restatement (bit-for-bit on dist/valid and on the per-view samples; the weighted mean only differs
