@@ -31,7 +31,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, q):
+def _worker(rank, world, port, n, q, block=None):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -56,24 +56,30 @@ def _worker(rank, world, port, n, q):
                     out[k].copy_(res[k]); res[k] = out[k]
             return res
 
-        got = eval_sharded(eval_fn, pts, ['dino_feats', 'mask'], gather=('dist', 'valid_mask', 'mask'), channels={'mask': 3})
+        got = eval_sharded(eval_fn, pts, ['dino_feats', 'mask'], gather=('dist', 'valid_mask', 'mask'), channels={'mask': 3},
+                           block=block)
         full = O.field_eval(pts.numpy(), sc.pose, sc.K, sc.depth, 60, 80, sc.maps, ['dino_feats', 'mask'])
-        s, e = got['shard']
-        assert (s, e) == shard_range(n, rank, world)
+        if block is None:
+            s, e = got['shard']
+            assert (s, e) == shard_range(n, rank, world)
+            mine = np.arange(s, e)
+        else:
+            mine = block_interleaved_index(n, rank, world, block).numpy()
+            assert np.array_equal(got['index'].numpy(), mine)
         ok = (np.array_equal(got['dist'].numpy(), full['dist']) and np.array_equal(got['valid_mask'].numpy(), full['valid_mask'])
-              and np.array_equal(got['mask'].numpy(), full['mask']) and np.array_equal(got['dino_feats'].numpy(), full['dino_feats'][s:e])
+              and np.array_equal(got['mask'].numpy(), full['mask']) and np.array_equal(got['dino_feats'].numpy(), full['dino_feats'][mine])
               and got['dist'].shape == (n,) and got['mask'].shape == (n, 3))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,n', [(2, 1000), (2, 1001), (3, 500)])
-def test_sharded_eval_over_gloo(world, n):
+@pytest.mark.parametrize('world,n,block', [(2, 1000, None), (2, 1001, None), (3, 500, None), (2, 1200, 50), (3, 900, 25)])
+def test_sharded_eval_over_gloo(world, n, block):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q, block)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
