@@ -198,6 +198,17 @@ def main():
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
+    # Watchdog: a whole run takes well under two minutes.  If a collective ever hangs (a rank died, a rendezvous
+    # problem), fail loudly instead of holding N GPUs until somebody's time limit expires.
+    limit = float(os.environ.get('D3F_BENCH_WATCHDOG_S', '900'))
+    def _abort():
+        sys.stderr.write(f'bench.py watchdog: no result after {limit:.0f} s, aborting\n')
+        sys.stderr.flush()
+        os._exit(3)
+    wd = threading.Timer(limit, _abort)
+    wd.daemon = True
+    wd.start()
+
     import torch
     import torch.distributed as dist
     from d3fields_b200 import Fusion, _native
