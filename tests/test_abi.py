@@ -57,3 +57,28 @@ def test_abi_version_and_argument_validation_without_gpu():
     assert rc == -1 and b'flag' in lib.d3f_last_error()
     with pytest.raises(_native.D3FError):
         _native.eval_device(99, 4, 4, 1, 1, 1, 1, 1, [], 1, 1, [], None, 0, 0.02, 0)
+
+
+def test_kernel_resource_contract():
+    """The walk's performance rests on compile-time properties that can be checked without a GPU: the wide tile
+    kernel keeps its 64-register texel cache without spilling at <= 128 registers (2 CTAs/SM), the light
+    instantiation fits 4 CTAs/SM (<= 64 registers), and the hot loop uses the uniform mask reduction (REDUX), 128-bit
+    streaming stores and L1 evict-last texel loads."""
+    build.build()
+    log = open(os.path.join(build.LIB_DIR, 'build.log')).read()
+    if 'field_tile_kernel' not in log:                      # library was current: rebuild once to get ptxas -v output
+        build.build(force=True)
+        log = open(os.path.join(build.LIB_DIR, 'build.log')).read()
+    blocks = re.findall(r"Function properties for (\S*field_tile_kernel\S*)\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                        r"(\d+) bytes spill loads\nptxas info\s*: Used (\d+) registers", log)
+    assert len(blocks) >= 6, 'expected six instantiations of field_tile_kernel in the ptxas log'
+    for name, stack, st, ld, regs in blocks:
+        wide = name.endswith('Lb1EEEvNS_10EvalParamsENS_6KeySetE')
+        assert int(st) == 0 and int(ld) == 0, f'{name}: spills'
+        assert int(regs) <= (128 if wide else 64), f'{name}: {regs} registers'
+    sass = subprocess.run(['cuobjdump', '-sass', build.LIB_PATH], capture_output=True, text=True).stdout
+    tile = sass[sass.index('field_tile_kernelILb0ELi0ELb1'):]
+    tile = tile[:tile.index('Function :', 10)] if 'Function :' in tile[10:] else tile
+    assert 'REDUX.OR' in tile, 'uniform mask reduction missing'
+    assert 'STG.E.EF.128' in tile, '128-bit streaming (evict-first) row stores missing'
+    assert tile.count('LDG.E.EL.128.CONSTANT') >= 16, 'L1 evict-last 128-bit texel loads missing'
