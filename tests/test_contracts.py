@@ -50,3 +50,14 @@ def test_graft_entry_build_runs_on_cpu():
     g.build()
     assert os.path.exists(os.path.join(ROOT, 'd3fields_b200', '_lib', 'libd3f.so'))
     assert os.path.exists(os.path.join(ROOT, 'oracle', '_build', 'libd3f_oracle.so'))
+
+
+def test_algorithmic_bytes_match_the_survey():
+    """bench.py's roofline numerator is SURVEY.md §8d's formula: 4.168 GB for cfg2a, 9.15 GB for cfg2b, 63.7 MB for cfg3 (u8)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    n, V, H, W = 1_000_000, 4, 480, 640
+    assert abs(bench.algorithmic_bytes(n, V, H, W, [(48, 64, 1024, 4)]) - 4.168e9) < 2e6
+    assert abs(bench.algorithmic_bytes(n, V, H, W, [(480, 640, 1024, 4)]) - 9.15e9) < 1e7
+    assert abs(bench.algorithmic_bytes(n, V, H, W, [(480, 640, 8, 1)]) - 63.7e6) < 1e5
+    assert bench.algorithmic_bytes(n, V, H, W, []) == 12 * n + V * H * W * 4 + 5 * n
