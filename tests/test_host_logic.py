@@ -90,3 +90,25 @@ def test_mask_injection_and_perception_delegation():
 def test_package_exports():
     for n in ('Fusion', 'create_init_grid', 'project_points_coords', 'interpolate_feats'):
         assert hasattr(d3fields_b200, n)
+
+
+def test_module_level_helpers_match_the_oracle_and_the_reference():
+    """project_points_coords / interpolate_feats are kept for callers that import them (reference fusion.py:32-77)."""
+    from d3fields_b200 import interpolate_feats, project_points_coords
+    from oracle import field_oracle as O
+    sc = S.make_scene(3, 40, 56, seed=9, feat=(5, 7, 6))
+    pts = np.concatenate([S.scattered_points(400, 9, sigma=0.3), S.adversarial_points(sc, 9, 4)])
+    p2, ok, z = project_points_coords(torch.from_numpy(pts), torch.from_numpy(sc.pose), torch.from_numpy(sc.K))
+    o2, ook, oz = O.project(pts, sc.pose, sc.K)
+    assert np.array_equal(p2.numpy().view(np.uint32), o2.view(np.uint32)) and np.array_equal(ok.numpy(), ook)
+    assert np.array_equal(z[..., 0].numpy().view(np.uint32), oz.view(np.uint32))
+    vol = torch.from_numpy(sc.maps['dino_feats']).permute(0, 3, 1, 2)
+    smp = interpolate_feats(vol, p2, h=40, w=56, padding_mode='zeros', align_corners=True, inter_mode='bilinear')
+    ref = O.sample_bilinear(sc.maps['dino_feats'], o2, 40, 56)
+    assert np.abs(smp.numpy() - ref).max() <= 1e-6
+    if RL.reference_available():
+        rf = RL.load_reference()
+        r2, rok, rz = rf.project_points_coords(torch.from_numpy(pts), torch.from_numpy(sc.pose), torch.from_numpy(sc.K))
+        assert torch.equal(r2, p2) and torch.equal(rok, ok) and torch.equal(rz, z)
+        rs = rf.interpolate_feats(vol, r2, h=40, w=56, padding_mode='zeros', align_corners=True, inter_mode='bilinear')
+        assert torch.equal(rs, smp)
