@@ -13,13 +13,19 @@ from . import build as _build
 
 D3F_MAX_VIEWS = 16
 D3F_MAX_KEYS = 8
+D3F_MAX_PEERS = 8
+D3F_IPC_HANDLE_BYTES = 64
 D3F_F32, D3F_U8 = 0, 1
 FLAG_EVAL_DIST, FLAG_RECIP_NORM = 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
+D3F_ETIMEOUT = -4
 
 # every symbol include/d3f.h declares (tests check the built library exports exactly these)
-SYMBOLS = ('d3f_eval', 'd3f_eval_host', 'd3f_eval_backward', 'd3f_pca_project', 'd3f_create_grid', 'd3f_abi_version',
-           'd3f_last_error', 'd3f_launch_count', 'd3f_last_variant')
+SYMBOLS = ('d3f_eval', 'd3f_eval_host', 'd3f_release_scratch', 'd3f_eval_ordered', 'd3f_bin_workspace_bytes',
+           'd3f_bin_order', 'd3f_sweep_select', 'd3f_comm_create', 'd3f_comm_connect', 'd3f_comm_destroy',
+           'd3f_comm_status', 'd3f_eval_allgather', 'd3f_comm_broadcast', 'd3f_eval_backward', 'd3f_pca_project',
+           'd3f_create_grid', 'd3f_abi_version', 'd3f_last_error', 'd3f_launch_count', 'd3f_last_variant',
+           'd3f_sizeof_key', 'd3f_sizeof_obs')
 
 
 class NativeLibraryError(RuntimeError):
@@ -39,7 +45,13 @@ class D3FObs(C.Structure):
 
 class D3FKey(C.Structure):
     _fields_ = [('data', C.c_void_p), ('dtype', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('C', C.c_int32),
+                ('stride_v', C.c_int64), ('stride_y', C.c_int64), ('stride_x', C.c_int64),
                 ('bias', C.c_void_p)]
+
+
+class D3FGrid(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('y', C.c_void_p), ('z', C.c_void_p),
+                ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -61,6 +73,9 @@ def load() -> C.CDLL:
         except Exception as e:  # no nvcc on this box: use a prebuilt library if there is one
             if not os.path.exists(path):
                 raise NativeLibraryError(f'libd3f.so is not built and cannot be built here: {e}') from e
+            import warnings
+            warnings.warn(f'{path} was built from different sources than the ones in {_build.CSRC} and cannot be '
+                          f'rebuilt here ({e}); loading it anyway — struct layouts are checked below', RuntimeWarning)
     if not os.path.exists(path):
         raise NativeLibraryError(f'{path} does not exist; run `python -m d3fields_b200.build`')
     try:
@@ -72,8 +87,33 @@ def load() -> C.CDLL:
                              C.POINTER(vp), C.POINTER(vp), u32, f32, vp]
     lib.d3f_eval.restype = C.c_int
     lib.d3f_eval_host.argtypes = [C.POINTER(D3FObs), vp, i64, C.POINTER(D3FKey), i32, vp, vp,
-                                  C.POINTER(vp), u32, f32]
+                                  C.POINTER(vp), u32, f32, vp]
     lib.d3f_eval_host.restype = C.c_int
+    lib.d3f_release_scratch.restype = C.c_int
+    lib.d3f_eval_ordered.argtypes = [C.POINTER(D3FObs), vp, i64, vp, C.POINTER(D3FKey), i32, vp, vp, C.POINTER(vp), u32, f32, vp]
+    lib.d3f_eval_ordered.restype = C.c_int
+    lib.d3f_bin_workspace_bytes.argtypes = [i64]
+    lib.d3f_bin_workspace_bytes.restype = i64
+    lib.d3f_bin_order.argtypes = [vp, i64, f32, vp, vp, i64, vp]
+    lib.d3f_bin_order.restype = C.c_int
+    lib.d3f_sweep_select.argtypes = [C.POINTER(D3FObs), C.POINTER(D3FGrid), vp, i64, C.POINTER(D3FKey), f32, f32, vp, vp,
+                                     i64, vp, vp, vp, u32, f32, vp]
+    lib.d3f_sweep_select.restype = C.c_int
+    lib.d3f_comm_create.argtypes = [i32, i32, i64, i64, C.POINTER(vp), vp]
+    lib.d3f_comm_create.restype = C.c_int
+    lib.d3f_comm_connect.argtypes = [vp, vp]
+    lib.d3f_comm_connect.restype = C.c_int
+    lib.d3f_comm_destroy.argtypes = [vp]
+    lib.d3f_comm_destroy.restype = C.c_int
+    lib.d3f_comm_status.argtypes = [vp, vp]
+    lib.d3f_comm_status.restype = C.c_int
+    lib.d3f_eval_allgather.argtypes = [vp, C.POINTER(D3FObs), vp, i64, C.POINTER(D3FKey), i32, C.POINTER(vp),
+                                       i64, i64, i64, u32, f32, vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.d3f_eval_allgather.restype = C.c_int
+    lib.d3f_comm_broadcast.argtypes = [vp, vp, i64, i32, vp]
+    lib.d3f_comm_broadcast.restype = C.c_int
+    lib.d3f_sizeof_key.restype = C.c_int
+    lib.d3f_sizeof_obs.restype = C.c_int
     lib.d3f_eval_backward.argtypes = [C.POINTER(D3FObs), vp, i64, C.POINTER(D3FKey), i32, C.POINTER(vp), vp, vp, u32, f32, vp]
     lib.d3f_eval_backward.restype = C.c_int
     lib.d3f_pca_project.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp]
@@ -88,6 +128,9 @@ def load() -> C.CDLL:
     got = lib.d3f_abi_version()
     if got != ABI_VERSION:
         raise NativeLibraryError(f'{path}: ABI version {got}, this package expects {ABI_VERSION}')
+    if lib.d3f_sizeof_key() != C.sizeof(D3FKey) or lib.d3f_sizeof_obs() != C.sizeof(D3FObs):
+        raise NativeLibraryError(f'{path}: D3FKey/D3FObs are {lib.d3f_sizeof_key()}/{lib.d3f_sizeof_obs()} bytes in the '
+                                 f'library but {C.sizeof(D3FKey)}/{C.sizeof(D3FObs)} in this binding (stale library?)')
     _lib = lib
     return lib
 
@@ -104,10 +147,17 @@ def _ptr_array(ptrs: Sequence[Optional[int]]):
     return arr
 
 
+def make_key(key: tuple) -> D3FKey:
+    """(data_ptr, dtype, h, w, C[, bias_ptr[, (stride_v, stride_y, stride_x)]]) -> D3FKey; strides in elements,
+    omitted = contiguous."""
+    sv, sy, sx = key[6] if len(key) > 6 and key[6] is not None else (0, 0, 0)
+    return D3FKey(key[0], key[1], key[2], key[3], key[4], sv, sy, sx, key[5] if len(key) > 5 else None)
+
+
 def _keys_array(keys: Sequence[tuple]):
     arr = (D3FKey * max(len(keys), 1))()
-    for i, key in enumerate(keys):          # (data_ptr, dtype, h, w, C[, bias_ptr])
-        arr[i] = D3FKey(key[0], key[1], key[2], key[3], key[4], key[5] if len(key) > 5 else None)
+    for i, key in enumerate(keys):
+        arr[i] = make_key(key)
     return arr
 
 
@@ -124,11 +174,84 @@ def eval_device(V: int, H: int, W: int, pose: int, K: int, depth: int, pts: int,
 
 def eval_host(V: int, H: int, W: int, pose: int, K: int, depth: int, pts_host: int, n: int,
               keys: Sequence[tuple], dist_host: int, valid_host: int, outs_host: Sequence[int],
-              flags: int, mu: float) -> None:
+              flags: int, mu: float, obs_stream: int = 0) -> None:
     lib = load()
     obs = D3FObs(V, H, W, pose, K, depth)
     _check(lib.d3f_eval_host(C.byref(obs), pts_host, n, _keys_array(keys), len(keys), dist_host, valid_host,
-                             _ptr_array(outs_host), flags, mu))
+                             _ptr_array(outs_host), flags, mu, obs_stream))
+
+
+def release_scratch() -> None:
+    _check(load().d3f_release_scratch())
+
+
+def eval_ordered(V: int, H: int, W: int, pose: int, K: int, depth: int, pts: int, n: int, order: int,
+                 keys: Sequence[tuple], dist: int, valid: int, outs: Sequence[int], flags: int, mu: float,
+                 stream: int) -> None:
+    lib = load()
+    obs = D3FObs(V, H, W, pose, K, depth)
+    _check(lib.d3f_eval_ordered(C.byref(obs), pts, n, order, _keys_array(keys), len(keys), dist, valid,
+                                _ptr_array(outs), flags, mu, stream))
+
+
+def bin_workspace_bytes(n: int) -> int:
+    return int(load().d3f_bin_workspace_bytes(n))
+
+
+def bin_order(pts: int, n: int, cell: float, order: int, workspace: int, workspace_bytes: int, stream: int) -> None:
+    _check(load().d3f_bin_order(pts, n, cell, order, workspace, workspace_bytes, stream))
+
+
+def sweep_select(V: int, H: int, W: int, pose: int, K: int, depth: int, grid: Optional[tuple], pts: Optional[int],
+                 n: int, mask_key: Optional[tuple], dist_thr: float, mask_thr: float, dist_out: Optional[int],
+                 valid_out: Optional[int], capacity: int, sel_count: Optional[int], sel_index: Optional[int],
+                 sel_inst: Optional[int], flags: int, mu: float, stream: int) -> None:
+    """grid: (x_ptr, y_ptr, z_ptr, nx, ny, nz) or None."""
+    lib = load()
+    obs = D3FObs(V, H, W, pose, K, depth)
+    g = D3FGrid(*grid) if grid is not None else None
+    k = make_key(mask_key) if mask_key is not None else None
+    _check(lib.d3f_sweep_select(C.byref(obs), C.byref(g) if g is not None else None, pts, n,
+                                C.byref(k) if k is not None else None, dist_thr, mask_thr, dist_out, valid_out,
+                                capacity, sel_count, sel_index, sel_inst, flags, mu, stream))
+
+
+def comm_create(rank: int, world: int, capacity_points: int, staging_bytes: int):
+    """-> (comm handle (int), 64-byte IPC handle of this rank's segment)."""
+    lib = load()
+    comm = C.c_void_p()
+    handle = (C.c_ubyte * D3F_IPC_HANDLE_BYTES)()
+    _check(lib.d3f_comm_create(rank, world, capacity_points, staging_bytes, C.byref(comm), handle))
+    return comm.value, bytes(handle)
+
+
+def comm_connect(comm: int, handles: bytes) -> None:
+    buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+    _check(load().d3f_comm_connect(comm, buf))
+
+
+def comm_destroy(comm: int) -> None:
+    _check(load().d3f_comm_destroy(comm))
+
+
+def comm_status(comm: int, stream: int) -> None:
+    _check(load().d3f_comm_status(comm, stream))
+
+
+def comm_broadcast(comm: int, buf: int, nbytes: int, root: int, stream: int) -> None:
+    _check(load().d3f_comm_broadcast(comm, buf, nbytes, root, stream))
+
+
+def eval_allgather(comm: int, V: int, H: int, W: int, pose: int, K: int, depth: int, pts: int, n: int,
+                   keys: Sequence[tuple], outs: Sequence[int], base: int, block: int, stride: int,
+                   flags: int, mu: float, stream: int):
+    """-> (dist_all_ptr, valid_all_ptr): local addresses of the gathered arrays of this call."""
+    lib = load()
+    obs = D3FObs(V, H, W, pose, K, depth)
+    d, v = C.c_void_p(), C.c_void_p()
+    _check(lib.d3f_eval_allgather(comm, C.byref(obs), pts, n, _keys_array(keys), len(keys), _ptr_array(outs),
+                                  base, block, stride, flags, mu, stream, C.byref(d), C.byref(v)))
+    return d.value, v.value
 
 
 def eval_backward(V: int, H: int, W: int, pose: int, K: int, depth: int, pts: int, n: int, keys: Sequence[tuple],

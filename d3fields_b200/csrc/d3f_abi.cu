@@ -15,6 +15,10 @@
 #include "d3f_tile.cuh"
 #include "d3f_aux.cuh"
 #include "d3f_backward.cuh"
+#include "d3f_sweep.cuh"
+#include "d3f_bin.cuh"
+#include "d3f_comm.cuh"
+#include <vector>
 
 namespace {
 
@@ -52,24 +56,43 @@ int check_device() {
 
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+// strides of a key with the contiguous default filled in
+struct KeyStrides { int64_t sv, sy, sx; };
+KeyStrides key_strides(const D3FKey& q) {
+    if (q.stride_v == 0 && q.stride_y == 0 && q.stride_x == 0)
+        return {(int64_t)q.h * q.w * q.C, (int64_t)q.w * q.C, (int64_t)q.C};
+    return {q.stride_v, q.stride_y, q.stride_x};
+}
+
+int validate_key(const D3FKey& q, int k) {
+    if (!q.data) return fail(D3F_EINVAL, "keys[%d].data is NULL", k);
+    if (q.dtype != D3F_F32 && q.dtype != D3F_U8) return fail(D3F_EINVAL, "keys[%d].dtype=%d unknown", k, q.dtype);
+    if (q.h < 1 || q.w < 1 || q.C < 1) return fail(D3F_EINVAL, "keys[%d] shape (%d,%d,%d) invalid", k, q.h, q.w, q.C);
+    if ((int64_t)q.h * q.w >= (1ll << 31)) return fail(D3F_EINVAL, "keys[%d] map too large", k);
+    const KeyStrides st = key_strides(q);
+    if (st.sv < 0 || st.sy < 0 || st.sx < 0) return fail(D3F_EINVAL, "keys[%d]: negative strides are not supported", k);
+    if (d3f::key_extent(q.h, q.w, q.C, st.sy, st.sx) >= (1ll << 31))
+        return fail(D3F_EINVAL, "keys[%d]: one view spans 2^31 elements or more", k);
+    return D3F_OK;
+}
+
 int validate(const D3FObs* obs, const void* pts, int64_t n, const D3FKey* keys, int32_t n_keys,
-             const void* dist, const void* valid, float* const* out, uint32_t flags, float mu) {
+             const void* dist, const void* valid, float* const* out, uint32_t flags, float mu,
+             bool need_compact = true) {
     if (!obs) return fail(D3F_EINVAL, "obs is NULL");
     if (obs->V < 1 || obs->V > D3F_MAX_VIEWS) return fail(D3F_EINVAL, "V=%d outside 1..%d", obs->V, D3F_MAX_VIEWS);
     if (obs->H < 2 || obs->W < 2) return fail(D3F_EINVAL, "image size %dx%d must be at least 2x2", obs->H, obs->W);
     if (!obs->pose || !obs->K || !obs->depth) return fail(D3F_EINVAL, "obs pose/K/depth pointer is NULL");
     if (n < 0) return fail(D3F_EINVAL, "n=%lld is negative", (long long)n);
-    if (n > 0 && (!pts || !dist || !valid)) return fail(D3F_EINVAL, "pts/dist/valid pointer is NULL");
+    if (n > 0 && (!pts || (need_compact && (!dist || !valid)))) return fail(D3F_EINVAL, "pts/dist/valid pointer is NULL");
     if (!(mu > 0.f)) return fail(D3F_EINVAL, "mu=%g must be positive", (double)mu);
     if (flags & ~(D3F_FLAG_EVAL_DIST | D3F_FLAG_RECIP_NORM)) return fail(D3F_EINVAL, "unknown flag bits 0x%x", flags);
     if (n_keys < 0 || n_keys > D3F_MAX_KEYS) return fail(D3F_EINVAL, "n_keys=%d outside 0..%d", n_keys, D3F_MAX_KEYS);
     if (n_keys > 0 && (!keys || !out)) return fail(D3F_EINVAL, "keys/out is NULL with n_keys=%d", n_keys);
     for (int k = 0; k < n_keys; ++k) {
         const D3FKey& q = keys[k];
-        if (!q.data) return fail(D3F_EINVAL, "keys[%d].data is NULL", k);
-        if (q.dtype != D3F_F32 && q.dtype != D3F_U8) return fail(D3F_EINVAL, "keys[%d].dtype=%d unknown", k, q.dtype);
-        if (q.h < 1 || q.w < 1 || q.C < 1) return fail(D3F_EINVAL, "keys[%d] shape (%d,%d,%d) invalid", k, q.h, q.w, q.C);
-        if ((int64_t)q.h * q.w >= (1ll << 31)) return fail(D3F_EINVAL, "keys[%d] map too large", k);
+        const int rk = validate_key(q, k);
+        if (rk) return rk;
         if (n > 0 && !out[k]) return fail(D3F_EINVAL, "out[%d] is NULL", k);
         if (q.bias && q.C >= 128) return fail(D3F_EINVAL, "keys[%d].bias is supported for C < 128 only", k);
         if (q.bias && q.C % 4 == 0 && !aligned(q.bias, 16)) return fail(D3F_EINVAL, "keys[%d].bias must be 16-byte aligned", k);
@@ -78,14 +101,32 @@ int validate(const D3FObs* obs, const void* pts, int64_t n, const D3FKey* keys, 
 }
 
 // Device-pointer evaluation shared by d3f_eval and the slabs of d3f_eval_host.
+__global__ void gather_only_kernel(const d3f::EvalParams ep) { d3f::gather_epilogue(ep); }
+
+template <bool RECIP, int VARIANT, bool WIDE>
+void launch_tile(bool ordered, dim3 grid, dim3 block, cudaStream_t st, const d3f::EvalParams& ep, const d3f::KeySet& ks) {
+    if (ordered) d3f::field_tile_kernel<RECIP, VARIANT, WIDE, true><<<grid, block, 0, st>>>(ep, ks);
+    else         d3f::field_tile_kernel<RECIP, VARIANT, WIDE, false><<<grid, block, 0, st>>>(ep, ks);
+}
+
 int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys, int32_t n_keys,
                 float* dist, uint8_t* valid, float* const* out, float* const* out_inter,
-                uint32_t flags, float mu, cudaStream_t st) {
-    if (n == 0) return D3F_OK;
+                uint32_t flags, float mu, cudaStream_t st,
+                const int32_t* order = nullptr, const d3f::GatherParams* gather = nullptr) {
     d3f::EvalParams ep;
+    memset(&ep, 0, sizeof(ep));
     ep.pts = pts; ep.depth = obs->depth; ep.pose = obs->pose; ep.K = obs->K;
     ep.dist = dist; ep.valid = valid; ep.n = n; ep.V = obs->V; ep.H = obs->H; ep.W = obs->W;
-    ep.mu = mu; ep.flags = flags;
+    ep.mu = mu; ep.flags = flags; ep.order = order;
+    if (gather) ep.g = *gather;
+    if (n == 0) {
+        if (gather) {                        // a rank without points still takes part in the epoch exchange
+            gather_only_kernel<<<1, 32, 0, st>>>(ep);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            D3F_CUDA(cudaGetLastError());
+        }
+        return D3F_OK;
+    }
     const bool eval_dist = (flags & D3F_FLAG_EVAL_DIST) != 0;
     const bool recip = (flags & D3F_FLAG_RECIP_NORM) != 0;
 
@@ -97,10 +138,12 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
         ks.k[k].data = keys[k].data; ks.k[k].out = out[k];
         ks.k[k].inter = (out_inter && out_inter[k]) ? out_inter[k] : nullptr;
         ks.k[k].h = keys[k].h; ks.k[k].w = keys[k].w; ks.k[k].C = keys[k].C;
+        const KeyStrides ksd = key_strides(keys[k]);
+        ks.k[k].sv = ksd.sv; ks.k[k].sy = (int32_t)ksd.sy; ks.k[k].sx = (int32_t)ksd.sx;
         ks.dtype[k] = keys[k].dtype;
         ks.k[k].bias = keys[k].bias;
         any_inter |= ks.k[k].inter != nullptr;
-        if (keys[k].C % 4 == 0) {
+        if (keys[k].C % 4 == 0 && ((ksd.sv | ksd.sy | ksd.sx) & 3) == 0) {
             const size_t a_in = keys[k].dtype == D3F_F32 ? 16 : 4;
             if (!aligned(keys[k].data, a_in) || !aligned(out[k], 16) || (ks.k[k].inter && !aligned(ks.k[k].inter, 16)))
                 return fail(D3F_EINVAL, "keys[%d]: map/out pointers must be 16-byte aligned when C %% 4 == 0", k);
@@ -108,31 +151,36 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
         g_variant[k] = "generic";
     }
     // production path: 128-point tiles, register-cached corner texels for wide float32 maps
+    auto is_wide = [&](int k) {
+        return d3f::key_is_wide(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w, ks.k[k].sv, ks.k[k].sy, ks.k[k].sx);
+    };
     bool tile_ok = obs->V <= d3f::TILE_V && !any_inter;
-    for (int k = 0; k < ks.n_keys; ++k) tile_ok &= ((int64_t)keys[k].h * keys[k].w < (1ll << 29));
+    for (int k = 0; k < ks.n_keys; ++k)
+        tile_ok &= d3f::key_fits_tile(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w, ks.k[k].sv, ks.k[k].sy, ks.k[k].sx);
+    if (any_inter && order) return fail(D3F_EINVAL, "per-view outputs are not available on an ordered launch");
     if (tile_ok) {
         const int64_t tiles = (n + d3f::TILE_PTS - 1) / d3f::TILE_PTS;
         if (tiles > 0x7fffffffll) return fail(D3F_EINVAL, "n=%lld too large for one launch", (long long)n);
         for (int k = 0; k < ks.n_keys; ++k)
-            g_variant[k] = d3f::key_is_wide(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w) ? "tile/wide" : "tile/narrow";
+            g_variant[k] = is_wide(k) ? "tile/wide" : "tile/narrow";
         dim3 grid((unsigned)tiles), block(d3f::TILE_THREADS);
         // L1 lookahead prefetch of cell changes pays only when the wide volume cannot stay L2-resident
         // (measured: cfg2b 5 GB volume 2.02 -> 1.87 ms; cfg2a 50 MB volume 0.80 -> 0.88 ms).  D3F_TILE_PREFETCH=0/1 overrides.
         static const int force = [] { const char* e = getenv("D3F_TILE_PREFETCH"); return e ? atoi(e) : -1; }();
         size_t wide_bytes = 0;
         for (int k = 0; k < ks.n_keys; ++k)
-            if (d3f::key_is_wide(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w))
-                wide_bytes += (size_t)obs->V * keys[k].h * keys[k].w * keys[k].C * 4;
+            if (is_wide(k)) wide_bytes += (size_t)obs->V * keys[k].h * keys[k].w * keys[k].C * 4;
         const bool prefetch = force >= 0 ? force != 0 : wide_bytes > (size_t)(64u << 20);
+        const bool ord = order != nullptr;
         if (wide_bytes == 0) {            // no register-cached walk needed: the light instantiation (4 CTAs/SM)
-            if (recip) d3f::field_tile_kernel<true, 0, false><<<grid, block, 0, st>>>(ep, ks);
-            else       d3f::field_tile_kernel<false, 0, false><<<grid, block, 0, st>>>(ep, ks);
+            if (recip) launch_tile<true, 0, false>(ord, grid, block, st, ep, ks);
+            else       launch_tile<false, 0, false>(ord, grid, block, st, ep, ks);
         } else if (recip) {
-            if (prefetch) d3f::field_tile_kernel<true, 4, true><<<grid, block, 0, st>>>(ep, ks);
-            else          d3f::field_tile_kernel<true, 0, true><<<grid, block, 0, st>>>(ep, ks);
+            if (prefetch) launch_tile<true, 4, true>(ord, grid, block, st, ep, ks);
+            else          launch_tile<true, 0, true>(ord, grid, block, st, ep, ks);
         } else {
-            if (prefetch) d3f::field_tile_kernel<false, 4, true><<<grid, block, 0, st>>>(ep, ks);
-            else          d3f::field_tile_kernel<false, 0, true><<<grid, block, 0, st>>>(ep, ks);
+            if (prefetch) launch_tile<false, 4, true>(ord, grid, block, st, ep, ks);
+            else          launch_tile<false, 0, true>(ord, grid, block, st, ep, ks);
         }
         g_launches.fetch_add(1, std::memory_order_relaxed);
         D3F_CUDA(cudaGetLastError());
@@ -167,16 +215,88 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
     return D3F_OK;
 }
 
-// ---- scratch for d3f_eval_host: streams + device slabs, grown on demand, kept until exit -----
+// ---- scratch for d3f_eval_host: streams + device slabs, pooled so concurrent callers never share one -----
 constexpr int HOST_STREAMS = 3;
 struct HostScratch {
     int dev = -1;
     cudaStream_t st[HOST_STREAMS] = {};
+    cudaEvent_t ready = nullptr;
     void* buf[HOST_STREAMS] = {};
     size_t cap[HOST_STREAMS] = {};
 };
 std::mutex g_scratch_mu;
-HostScratch g_scratch;
+std::vector<HostScratch*> g_scratch_free;
+
+void scratch_free(HostScratch* sc) {
+    for (int i = 0; i < HOST_STREAMS; ++i) {
+        if (sc->buf[i]) cudaFree(sc->buf[i]);
+        if (sc->st[i]) cudaStreamDestroy(sc->st[i]);
+    }
+    if (sc->ready) cudaEventDestroy(sc->ready);
+    delete sc;
+}
+
+HostScratch* scratch_acquire(int dev) {
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        for (size_t i = 0; i < g_scratch_free.size(); ++i)
+            if (g_scratch_free[i]->dev == dev) {
+                HostScratch* sc = g_scratch_free[i];
+                g_scratch_free.erase(g_scratch_free.begin() + i);
+                return sc;
+            }
+    }
+    HostScratch* sc = new HostScratch;
+    sc->dev = dev;
+    bool ok = cudaEventCreateWithFlags(&sc->ready, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < HOST_STREAMS && ok; ++i)
+        ok = cudaStreamCreateWithFlags(&sc->st[i], cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) { scratch_free(sc); return nullptr; }
+    return sc;
+}
+
+void scratch_release(HostScratch* sc) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    g_scratch_free.push_back(sc);
+}
+
+// The slab loop of d3f_eval_host; the caller synchronises the scratch streams whatever this returns.
+int eval_host_slabs(HostScratch& sc, const D3FObs* obs, const float* pts_host, int64_t n, const D3FKey* keys, int nk,
+                    float* dist_host, uint8_t* valid_host, float* const* out_host, uint32_t flags, float mu,
+                    int64_t slab, size_t need) {
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    for (int i = 0; i < HOST_STREAMS; ++i) {
+        if (sc.cap[i] < need) {
+            if (sc.buf[i]) D3F_CUDA(cudaFree(sc.buf[i]));
+            sc.buf[i] = nullptr; sc.cap[i] = 0;
+            D3F_CUDA(cudaMalloc(&sc.buf[i], need));
+            sc.cap[i] = need;
+        }
+    }
+    int it = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += slab, ++it) {
+        const int64_t m = (n - s0 < slab) ? (n - s0) : slab;
+        const int si = it % HOST_STREAMS;
+        cudaStream_t st = sc.st[si];
+        char* b = static_cast<char*>(sc.buf[si]);
+        float* d_pts = reinterpret_cast<float*>(b);      b += up((size_t)slab * 12);
+        float* d_dist = reinterpret_cast<float*>(b);     b += up((size_t)slab * 4);
+        uint8_t* d_valid = reinterpret_cast<uint8_t*>(b); b += up((size_t)slab);
+        float* d_out[D3F_MAX_KEYS] = {};
+        for (int k = 0; k < nk; ++k) { d_out[k] = reinterpret_cast<float*>(b); b += up((size_t)slab * keys[k].C * 4); }
+        // stream order on `st` protects the slab buffers: the previous use of this slab ended
+        // with its D2H copies on the same stream
+        D3F_CUDA(cudaMemcpyAsync(d_pts, pts_host + s0 * 3, (size_t)m * 12, cudaMemcpyHostToDevice, st));
+        const int rc = launch_eval(obs, d_pts, m, keys, nk, d_dist, d_valid, d_out, nullptr, flags, mu, st);
+        if (rc) return rc;
+        D3F_CUDA(cudaMemcpyAsync(dist_host + s0, d_dist, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        D3F_CUDA(cudaMemcpyAsync(valid_host + s0, d_valid, (size_t)m, cudaMemcpyDeviceToHost, st));
+        for (int k = 0; k < nk; ++k)
+            D3F_CUDA(cudaMemcpyAsync(out_host[k] + (size_t)s0 * keys[k].C, d_out[k], (size_t)m * keys[k].C * 4,
+                                     cudaMemcpyDeviceToHost, st));
+    }
+    return D3F_OK;
+}
 
 }  // namespace
 
@@ -186,6 +306,8 @@ int d3f_abi_version(void) { return D3F_ABI_VERSION; }
 const char* d3f_last_error(void) { return g_err; }
 int64_t d3f_launch_count(void) { return g_launches.load(); }
 const char* d3f_last_variant(int32_t k) { return (k >= 0 && k < D3F_MAX_KEYS && g_variant[k]) ? g_variant[k] : ""; }
+int d3f_sizeof_key(void) { return (int)sizeof(D3FKey); }
+int d3f_sizeof_obs(void) { return (int)sizeof(D3FObs); }
 
 int d3f_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys, int32_t n_keys,
              float* dist, uint8_t* valid, float* const* out, float* const* out_inter,
@@ -198,7 +320,8 @@ int d3f_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys,
 }
 
 int d3f_eval_host(const D3FObs* obs, const float* pts_host, int64_t n, const D3FKey* keys, int32_t n_keys,
-                  float* dist_host, uint8_t* valid_host, float* const* out_host, uint32_t flags, float mu) {
+                  float* dist_host, uint8_t* valid_host, float* const* out_host, uint32_t flags, float mu,
+                  void* obs_stream) {
     int rc = validate(obs, pts_host, n, keys, n_keys, dist_host, valid_host, out_host, flags, mu);
     if (rc) return rc;
     if ((rc = check_device())) return rc;
@@ -219,53 +342,280 @@ int d3f_eval_host(const D3FObs* obs, const float* pts_host, int64_t n, const D3F
     const size_t need = up((size_t)slab * 12) + up((size_t)slab * 4) + up((size_t)slab) +
                         [&] { size_t s = 0; for (int k = 0; k < nk; ++k) s += up((size_t)slab * keys[k].C * 4); return s; }();
 
-    std::lock_guard<std::mutex> lock(g_scratch_mu);
     int dev = 0;
     D3F_CUDA(cudaGetDevice(&dev));
-    HostScratch& sc = g_scratch;
-    if (sc.dev != dev) {
-        for (int i = 0; i < HOST_STREAMS; ++i) {
-            if (sc.buf[i]) cudaFree(sc.buf[i]);
-            sc.buf[i] = nullptr; sc.cap[i] = 0;
-            if (sc.st[i]) cudaStreamDestroy(sc.st[i]);
-            D3F_CUDA(cudaStreamCreateWithFlags(&sc.st[i], cudaStreamNonBlocking));
-        }
-        sc.dev = dev;
-    }
+    HostScratch* sc = scratch_acquire(dev);
+    if (!sc) return fail(D3F_ECUDA, "d3f_eval_host: cannot create scratch streams");
+    // order the internal streams after whatever wrote the observation (no device-wide synchronisation)
+    cudaError_t e = cudaEventRecord(sc->ready, static_cast<cudaStream_t>(obs_stream));
+    for (int i = 0; i < HOST_STREAMS && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(sc->st[i], sc->ready, 0);
+    if (e != cudaSuccess) rc = fail(D3F_ECUDA, "d3f_eval_host: stream ordering failed: %s", cudaGetErrorString(e));
+    else rc = eval_host_slabs(*sc, obs, pts_host, n, keys, nk, dist_host, valid_host, out_host, flags, mu, slab, need);
+    // synchronous also on failure: no copy into the caller's buffers may still be in flight when we return
     for (int i = 0; i < HOST_STREAMS; ++i) {
-        if (sc.cap[i] < need) {
-            if (sc.buf[i]) D3F_CUDA(cudaFree(sc.buf[i]));
-            sc.buf[i] = nullptr; sc.cap[i] = 0;
-            D3F_CUDA(cudaMalloc(&sc.buf[i], need));
-            sc.cap[i] = need;
+        const cudaError_t es = cudaStreamSynchronize(sc->st[i]);
+        if (es != cudaSuccess && rc == D3F_OK) rc = fail(D3F_ECUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(es));
+    }
+    scratch_release(sc);
+    return rc;
+}
+
+int d3f_release_scratch(void) {
+    int dev = 0;
+    D3F_CUDA(cudaGetDevice(&dev));
+    std::vector<HostScratch*> mine;
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        for (size_t i = 0; i < g_scratch_free.size();) {
+            if (g_scratch_free[i]->dev == dev) { mine.push_back(g_scratch_free[i]); g_scratch_free.erase(g_scratch_free.begin() + i); }
+            else ++i;
         }
     }
-    // the observation may have been written on another stream by the caller: make it visible
-    D3F_CUDA(cudaDeviceSynchronize());
+    for (HostScratch* sc : mine) scratch_free(sc);
+    return D3F_OK;
+}
 
-    int it = 0;
-    for (int64_t s0 = 0; s0 < n; s0 += slab, ++it) {
-        const int64_t m = (n - s0 < slab) ? (n - s0) : slab;
-        const int si = it % HOST_STREAMS;
-        cudaStream_t st = sc.st[si];
-        char* b = static_cast<char*>(sc.buf[si]);
-        float* d_pts = reinterpret_cast<float*>(b);      b += up((size_t)slab * 12);
-        float* d_dist = reinterpret_cast<float*>(b);     b += up((size_t)slab * 4);
-        uint8_t* d_valid = reinterpret_cast<uint8_t*>(b); b += up((size_t)slab);
-        float* d_out[D3F_MAX_KEYS] = {};
-        for (int k = 0; k < nk; ++k) { d_out[k] = reinterpret_cast<float*>(b); b += up((size_t)slab * keys[k].C * 4); }
-        // stream order on `st` protects the slab buffers: the previous use of this slab ended
-        // with its D2H copies on the same stream
-        D3F_CUDA(cudaMemcpyAsync(d_pts, pts_host + s0 * 3, (size_t)m * 12, cudaMemcpyHostToDevice, st));
-        rc = launch_eval(obs, d_pts, m, keys, nk, d_dist, d_valid, d_out, nullptr, flags, mu, st);
-        if (rc) return rc;
-        D3F_CUDA(cudaMemcpyAsync(dist_host + s0, d_dist, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-        D3F_CUDA(cudaMemcpyAsync(valid_host + s0, d_valid, (size_t)m, cudaMemcpyDeviceToHost, st));
-        for (int k = 0; k < nk; ++k)
-            D3F_CUDA(cudaMemcpyAsync(out_host[k] + (size_t)s0 * keys[k].C, d_out[k], (size_t)m * keys[k].C * 4,
-                                     cudaMemcpyDeviceToHost, st));
+int d3f_eval_ordered(const D3FObs* obs, const float* pts, int64_t n, const int32_t* order,
+                     const D3FKey* keys, int32_t n_keys, float* dist, uint8_t* valid, float* const* out,
+                     uint32_t flags, float mu, void* stream) {
+    int rc = validate(obs, pts, n, keys, n_keys, dist, valid, out, flags, mu);
+    if (rc) return rc;
+    if (n > 0 && !order) return fail(D3F_EINVAL, "order is NULL");
+    if (n >= (1ll << 31)) return fail(D3F_EINVAL, "ordered launches index points with int32: n=%lld too large", (long long)n);
+    if ((rc = check_device())) return rc;
+    return launch_eval(obs, pts, n, keys, n_keys, dist, valid, out, nullptr, flags, mu,
+                       static_cast<cudaStream_t>(stream), order, nullptr);
+}
+
+int64_t d3f_bin_workspace_bytes(int64_t n) { return (int64_t)d3f::bin_workspace_bytes(n); }
+
+int d3f_bin_order(const float* pts, int64_t n, float cell, int32_t* order, void* workspace, int64_t workspace_bytes,
+                  void* stream) {
+    if (n < 0 || n >= (1ll << 31)) return fail(D3F_EINVAL, "bin: n=%lld outside 0..2^31", (long long)n);
+    if (n > 0 && (!pts || !order || !workspace)) return fail(D3F_EINVAL, "bin: NULL pointer");
+    if (!(cell > 0.f)) return fail(D3F_EINVAL, "bin: cell=%g must be positive", (double)cell);
+    if (workspace_bytes < (int64_t)d3f::bin_workspace_bytes(n))
+        return fail(D3F_EINVAL, "bin: workspace of %lld bytes, %lld needed", (long long)workspace_bytes, (long long)d3f::bin_workspace_bytes(n));
+    if (!aligned(workspace, 16)) return fail(D3F_EINVAL, "bin: workspace must be 16-byte aligned");
+    int rc = check_device();
+    if (rc) return rc;
+    if (n == 0) return D3F_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    int* bbox = reinterpret_cast<int*>(ws);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(ws + 256);
+    uint32_t* block_base = hist + d3f::BIN_COUNT;
+    uint32_t* keys = block_base + d3f::BIN_SCAN_BLOCKS;
+    D3F_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * ((size_t)d3f::BIN_COUNT + d3f::BIN_SCAN_BLOCKS), st));
+    const unsigned blocks = (unsigned)((n + d3f::BIN_THREADS - 1) / d3f::BIN_THREADS);
+    d3f::bin_init_kernel<<<1, 32, 0, st>>>(bbox);
+    d3f::bin_bbox_kernel<<<blocks < 1184u ? blocks : 1184u, d3f::BIN_THREADS, 0, st>>>(pts, n, bbox);
+    d3f::bin_key_kernel<<<blocks, d3f::BIN_THREADS, 0, st>>>(pts, n, cell, bbox, keys, hist);
+    d3f::bin_scan_kernel<<<d3f::BIN_SCAN_BLOCKS, d3f::BIN_SCAN_THREADS, 0, st>>>(hist, block_base);
+    d3f::bin_scan_base_kernel<<<1, d3f::BIN_SCAN_BLOCKS, 0, st>>>(block_base);
+    d3f::bin_scatter_kernel<<<blocks, d3f::BIN_THREADS, 0, st>>>(keys, n, hist, block_base, order);
+    g_launches.fetch_add(6, std::memory_order_relaxed);
+    D3F_CUDA(cudaGetLastError());
+    return D3F_OK;
+}
+
+int d3f_sweep_select(const D3FObs* obs, const D3FGrid* grid, const float* pts, int64_t n,
+                     const D3FKey* mask_key, float dist_threshold, float mask_threshold,
+                     float* dist_out, uint8_t* valid_out,
+                     int64_t capacity, int64_t* sel_count, int32_t* sel_index, int32_t* sel_inst,
+                     uint32_t flags, float mu, void* stream) {
+    if (!obs) return fail(D3F_EINVAL, "obs is NULL");
+    if (obs->V < 1 || obs->V > D3F_MAX_VIEWS) return fail(D3F_EINVAL, "V=%d outside 1..%d", obs->V, D3F_MAX_VIEWS);
+    if (obs->H < 2 || obs->W < 2) return fail(D3F_EINVAL, "image size %dx%d must be at least 2x2", obs->H, obs->W);
+    if (!obs->pose || !obs->K || !obs->depth) return fail(D3F_EINVAL, "obs pose/K/depth pointer is NULL");
+    if (!(mu > 0.f)) return fail(D3F_EINVAL, "mu=%g must be positive", (double)mu);
+    if (flags & ~D3F_FLAG_RECIP_NORM) return fail(D3F_EINVAL, "sweep: unsupported flag bits 0x%x", flags);
+    if (grid) {
+        if (grid->nx < 0 || grid->ny < 0 || grid->nz < 0) return fail(D3F_EINVAL, "sweep: negative grid size");
+        if ((int64_t)grid->nx * grid->ny * grid->nz != n) return fail(D3F_EINVAL, "sweep: n=%lld is not nx*ny*nz", (long long)n);
+        if (n > 0 && (!grid->x || !grid->y || !grid->z)) return fail(D3F_EINVAL, "sweep: grid axis pointer is NULL");
+    } else if (n > 0 && !pts) {
+        return fail(D3F_EINVAL, "sweep: neither a grid nor pts");
     }
-    for (int i = 0; i < HOST_STREAMS; ++i) D3F_CUDA(cudaStreamSynchronize(sc.st[i]));
+    if (n < 0 || n >= (1ll << 31)) return fail(D3F_EINVAL, "sweep: n=%lld outside 0..2^31 (survivors are int32 indices)", (long long)n);
+    d3f::SweepParams sp;
+    memset(&sp, 0, sizeof(sp));
+    if (mask_key) {
+        int rc = validate_key(*mask_key, 0);
+        if (rc) return rc;
+        if (mask_key->C > d3f::SWEEP_MAX_INST) return fail(D3F_EINVAL, "sweep: num_inst=%d above %d", mask_key->C, d3f::SWEEP_MAX_INST);
+        if (capacity < 0 || !sel_count || (capacity > 0 && (!sel_index || !sel_inst)))
+            return fail(D3F_EINVAL, "sweep: selection outputs missing");
+        const KeyStrides ksd = key_strides(*mask_key);
+        sp.mask = mask_key->data; sp.mdtype = mask_key->dtype; sp.mh = mask_key->h; sp.mw = mask_key->w; sp.mC = mask_key->C;
+        sp.msv = ksd.sv; sp.msy = (int32_t)ksd.sy; sp.msx = (int32_t)ksd.sx;
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    if (n == 0) return D3F_OK;
+    if (grid) { sp.gx = grid->x; sp.gy = grid->y; sp.gz = grid->z; sp.nx = grid->nx; sp.ny = grid->ny; sp.nz = grid->nz; }
+    sp.dist_thr = dist_threshold; sp.mask_thr = mask_threshold;
+    sp.dist_out = dist_out; sp.valid_out = valid_out;
+    sp.capacity = capacity; sp.count = reinterpret_cast<unsigned long long*>(sel_count);
+    sp.sel_index = sel_index; sp.sel_inst = sel_inst;
+    d3f::EvalParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.pts = pts; ep.depth = obs->depth; ep.pose = obs->pose; ep.K = obs->K; ep.n = n;
+    ep.V = obs->V; ep.H = obs->H; ep.W = obs->W; ep.mu = mu; ep.flags = flags;
+    const unsigned blocks = (unsigned)((n + d3f::SWEEP_THREADS - 1) / d3f::SWEEP_THREADS);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (flags & D3F_FLAG_RECIP_NORM) d3f::field_sweep_kernel<true><<<blocks, d3f::SWEEP_THREADS, 0, st>>>(ep, sp);
+    else                             d3f::field_sweep_kernel<false><<<blocks, d3f::SWEEP_THREADS, 0, st>>>(ep, sp);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    D3F_CUDA(cudaGetLastError());
+    return D3F_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------------------
+int d3f_comm_create(int32_t rank, int32_t world, int64_t capacity_points, int64_t staging_bytes,
+                    D3FComm** comm, void* handle_out) {
+    if (!comm) return fail(D3F_EINVAL, "comm is NULL");
+    if (world < 1 || world > D3F_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(D3F_EINVAL, "comm: rank %d / world %d outside 1..%d", rank, world, D3F_MAX_PEERS);
+    if (capacity_points < 0 || staging_bytes < 0) return fail(D3F_EINVAL, "comm: negative capacity");
+    if (world > 1 && !handle_out) return fail(D3F_EINVAL, "comm: handle_out is NULL");
+    int rc = check_device();
+    if (rc) return rc;
+    D3FComm* c = new D3FComm;
+    c->rank = rank; c->world = world; c->capacity = capacity_points;
+    D3F_CUDA(cudaGetDevice(&c->dev));
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t off = 4096;
+    for (int b = 0; b < 2; ++b) {
+        c->off_dist[b] = off;  off += up((size_t)capacity_points * 4);
+        c->off_valid[b] = off; off += up((size_t)capacity_points);
+    }
+    c->off_staging = off;
+    c->staging_bytes = up((size_t)staging_bytes);
+    off += c->staging_bytes;
+    c->seg_bytes = off;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, c->seg_bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, 4096);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && world > 1) e = cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle_out), p);
+    if (e != cudaSuccess) {
+        if (p) cudaFree(p);
+        delete c;
+        return fail(D3F_ECUDA, "comm: segment of %zu bytes: %s", off, cudaGetErrorString(e));
+    }
+    c->seg[rank] = static_cast<char*>(p);
+    c->connected = world == 1;
+    *comm = c;
+    return D3F_OK;
+}
+
+int d3f_comm_connect(D3FComm* c, const void* handles) {
+    if (!c) return fail(D3F_EINVAL, "comm is NULL");
+    if (c->connected) return D3F_OK;
+    if (!handles) return fail(D3F_EINVAL, "comm: handles is NULL");
+    const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handles);
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(D3F_ECUDA, "comm: cannot map the segment of rank %d (CUDA IPC / peer access): %s", r, cudaGetErrorString(e));
+        }
+        c->seg[r] = static_cast<char*>(p);
+    }
+    c->connected = true;
+    return D3F_OK;
+}
+
+int d3f_comm_destroy(D3FComm* c) {
+    if (!c) return D3F_OK;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r) {
+        if (!c->seg[r]) continue;
+        if (r == c->rank) cudaFree(c->seg[r]);
+        else cudaIpcCloseMemHandle(c->seg[r]);
+    }
+    delete c;
+    return D3F_OK;
+}
+
+int d3f_comm_status(D3FComm* c, void* stream) {
+    if (!c) return fail(D3F_EINVAL, "comm is NULL");
+    D3F_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    uint32_t err = 0;
+    D3F_CUDA(cudaMemcpy(&err, &c->hdr(c->rank)->error, 4, cudaMemcpyDeviceToHost));
+    if (err) return fail(D3F_ETIMEOUT, "comm: a wait on a peer of rank %d timed out (a rank did not join the collective)", c->rank);
+    return D3F_OK;
+}
+
+int d3f_eval_allgather(D3FComm* c, const D3FObs* obs, const float* pts, int64_t n,
+                       const D3FKey* keys, int32_t n_keys, float* const* out,
+                       int64_t gather_base, int64_t gather_block, int64_t gather_stride,
+                       uint32_t flags, float mu, void* stream, float** dist_all, uint8_t** valid_all) {
+    if (!c || !c->connected) return fail(D3F_EINVAL, "comm is NULL or not connected");
+    int rc = validate(obs, pts, n, keys, n_keys, nullptr, nullptr, out, flags, mu, false);
+    if (rc) return rc;
+    if (gather_block < 1 || gather_base < 0 || gather_stride < 0) return fail(D3F_EINVAL, "gather: bad base/block/stride");
+    if (n > 0) {
+        const int64_t last = gather_base + ((n - 1) / gather_block) * gather_stride + (n - 1) % gather_block;
+        if (last >= c->capacity) return fail(D3F_EINVAL, "gather: index %lld outside the communicator's capacity %lld", (long long)last, (long long)c->capacity);
+    }
+    if ((rc = check_device())) return rc;
+    const uint32_t epoch = ++c->epoch;
+    const int b = (int)(epoch & 1u);
+    d3f::GatherParams g;
+    memset(&g, 0, sizeof(g));
+    for (int r = 0; r < c->world; ++r) {
+        g.dist[r] = reinterpret_cast<float*>(c->seg[r] + c->off_dist[b]);
+        g.valid[r] = reinterpret_cast<uint8_t*>(c->seg[r] + c->off_valid[b]);
+        g.flag[r] = &c->hdr(r)->gather_flag[c->rank];
+    }
+    g.my_flags = c->hdr(c->rank)->gather_flag;
+    g.counter = &c->hdr(c->rank)->counter;
+    g.error = &c->hdr(c->rank)->error;
+    g.base = gather_base; g.block = gather_block; g.stride = gather_stride;
+    g.epoch = epoch; g.world = c->world;
+    if (dist_all) *dist_all = g.dist[c->rank];
+    if (valid_all) *valid_all = g.valid[c->rank];
+    return launch_eval(obs, pts, n, keys, n_keys, nullptr, nullptr, out, nullptr, flags, mu,
+                       static_cast<cudaStream_t>(stream), nullptr, &g);
+}
+
+int d3f_comm_broadcast(D3FComm* c, void* buf, int64_t bytes, int32_t root, void* stream) {
+    if (!c || !c->connected) return fail(D3F_EINVAL, "comm is NULL or not connected");
+    if (root < 0 || root >= c->world) return fail(D3F_EINVAL, "broadcast: root %d outside 0..%d", root, c->world - 1);
+    if (bytes < 0 || (bytes > 0 && !buf)) return fail(D3F_EINVAL, "broadcast: bad buffer");
+    if (c->world == 1 || bytes == 0) return D3F_OK;
+    if (c->staging_bytes == 0) return fail(D3F_EINVAL, "broadcast: the communicator was created without staging");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    d3f::CommHeader* me = c->hdr(c->rank);
+    d3f::FlagTargets everyone, ready;
+    memset(&everyone, 0, sizeof(everyone));
+    memset(&ready, 0, sizeof(ready));
+    for (int r = 0; r < c->world; ++r) {
+        everyone.p[everyone.count++] = &c->hdr(r)->bcast_taken[c->rank];
+        if (r != c->rank) ready.p[ready.count++] = &c->hdr(r)->bcast_ready;
+    }
+    char* src = static_cast<char*>(buf);
+    for (int64_t off = 0; off < bytes; off += (int64_t)c->staging_bytes) {
+        const size_t m = (size_t)((bytes - off < (int64_t)c->staging_bytes) ? bytes - off : (int64_t)c->staging_bytes);
+        const uint32_t seq = ++c->bcast_seq;
+        if (c->rank == root) {
+            // every rank must be done with the previous chunk before its staging area is overwritten
+            d3f::comm_wait_kernel<<<1, 32, 0, st>>>(me->bcast_taken, c->world, seq - 1, &me->error);
+            for (int r = 0; r < c->world; ++r)
+                if (r != root) D3F_CUDA(cudaMemcpyAsync(c->seg[r] + c->off_staging, src + off, m, cudaMemcpyDefault, st));
+            d3f::comm_signal_kernel<<<1, 32, 0, st>>>(ready, seq);
+        } else {
+            d3f::comm_wait_kernel<<<1, 32, 0, st>>>(&me->bcast_ready, 1, seq, &me->error);
+            D3F_CUDA(cudaMemcpyAsync(src + off, c->seg[c->rank] + c->off_staging, m, cudaMemcpyDeviceToDevice, st));
+        }
+        d3f::comm_signal_kernel<<<1, 32, 0, st>>>(everyone, seq);
+        g_launches.fetch_add(c->rank == root ? 3 : 2, std::memory_order_relaxed);
+    }
+    D3F_CUDA(cudaGetLastError());
     return D3F_OK;
 }
 
@@ -274,6 +624,7 @@ int d3f_eval_backward(const D3FObs* obs, const float* pts, int64_t n, const D3FK
                       uint32_t flags, float mu, void* stream) {
     if (!obs) return fail(D3F_EINVAL, "obs is NULL");
     if (obs->V < 1 || obs->V > D3F_MAX_VIEWS) return fail(D3F_EINVAL, "V=%d outside 1..%d", obs->V, D3F_MAX_VIEWS);
+    if (obs->H < 2 || obs->W < 2) return fail(D3F_EINVAL, "image size %dx%d must be at least 2x2", obs->H, obs->W);
     if (!obs->pose || !obs->K || !obs->depth) return fail(D3F_EINVAL, "obs pose/K/depth pointer is NULL");
     if (n < 0 || (n > 0 && (!pts || !grad_pts))) return fail(D3F_EINVAL, "backward: bad n / NULL pts or grad_pts");
     if (!(mu > 0.f)) return fail(D3F_EINVAL, "mu=%g must be positive", (double)mu);
@@ -284,10 +635,14 @@ int d3f_eval_backward(const D3FObs* obs, const float* pts, int64_t n, const D3FK
     memset(&ks, 0, sizeof(ks));
     ks.n_keys = n_keys;
     for (int k = 0; k < n_keys; ++k) {
-        if (!keys[k].data || (keys[k].dtype != D3F_F32 && keys[k].dtype != D3F_U8) || keys[k].h < 1 || keys[k].w < 1 || keys[k].C < 1)
-            return fail(D3F_EINVAL, "backward: keys[%d] invalid", k);
+        const int rk = validate_key(keys[k], k);
+        if (rk) return rk;
+        const KeyStrides ksd = key_strides(keys[k]);
         ks.data[k] = keys[k].data; ks.grad[k] = grad_out[k]; ks.dtype[k] = keys[k].dtype;
         ks.h[k] = keys[k].h; ks.w[k] = keys[k].w; ks.C[k] = keys[k].C;
+        ks.sv[k] = ksd.sv; ks.sy[k] = (int32_t)ksd.sy; ks.sx[k] = (int32_t)ksd.sx;
+        ks.vec4[k] = keys[k].dtype == D3F_F32 && keys[k].C % 4 == 0 && ((ksd.sv | ksd.sy | ksd.sx) & 3) == 0 &&
+                     aligned(keys[k].data, 16) && aligned(grad_out[k], 16);
     }
     int rc = check_device();
     if (rc) return rc;

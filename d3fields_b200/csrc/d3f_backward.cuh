@@ -29,6 +29,9 @@ struct BwdKeySet {
     const float* grad[D3F_MAX_KEYS];     // (n,C) upstream gradient of the key's output, or nullptr
     int32_t dtype[D3F_MAX_KEYS];
     int32_t h[D3F_MAX_KEYS], w[D3F_MAX_KEYS], C[D3F_MAX_KEYS];
+    int64_t sv[D3F_MAX_KEYS];            // element strides of the view / row / texel axes (channel stride 1)
+    int32_t sy[D3F_MAX_KEYS], sx[D3F_MAX_KEYS];
+    int32_t vec4[D3F_MAX_KEYS];          // 1: float32 map, C % 4 == 0, 16-byte aligned map and gradient -> 128-bit loads
     int32_t n_keys;
 };
 
@@ -96,26 +99,49 @@ field_backward_kernel(const EvalParams ep, const BwdKeySet ks, const float* __re
             const int y0c = (int)fminf(fmaxf(y0, 0.f), ym), y1c = (int)fminf(fmaxf(y1, 0.f), ym);
             const float m00 = (x0ok && y0ok) ? 1.f : 0.f, m01 = (x1ok && y0ok) ? 1.f : 0.f;
             const float m10 = (x0ok && y1ok) ? 1.f : 0.f, m11 = (x1ok && y1ok) ? 1.f : 0.f;
-            const size_t vbase = (size_t)v * h * w;
-            const size_t o00 = (vbase + (size_t)y0c * w + x0c) * C, o01 = (vbase + (size_t)y0c * w + x1c) * C;
-            const size_t o10 = (vbase + (size_t)y1c * w + x0c) * C, o11 = (vbase + (size_t)y1c * w + x1c) * C;
+            const size_t vbase = (size_t)v * (size_t)ks.sv[k];
+            const size_t sy = (size_t)ks.sy[k], sx = (size_t)ks.sx[k];
+            const size_t o00 = vbase + (size_t)y0c * sy + (size_t)x0c * sx, o01 = vbase + (size_t)y0c * sy + (size_t)x1c * sx;
+            const size_t o10 = vbase + (size_t)y1c * sy + (size_t)x0c * sx, o11 = vbase + (size_t)y1c * sy + (size_t)x1c * sx;
             const float* g = ks.grad[k] + (size_t)i * C;
+            const float ex = 1.f - wx, ey = 1.f - wy;
             float s_ix = 0.f, s_iy = 0.f, s_r = 0.f;
-            for (int c = lane; c < C; c += 32) {
-                float f00, f01, f10, f11;
-                if (ks.dtype[k] == D3F_F32) {
-                    const float* vol = static_cast<const float*>(ks.data[k]);
-                    f00 = __ldg(vol + o00 + c); f01 = __ldg(vol + o01 + c); f10 = __ldg(vol + o10 + c); f11 = __ldg(vol + o11 + c);
-                } else {
-                    const uint8_t* vol = static_cast<const uint8_t*>(ks.data[k]);
-                    f00 = (float)__ldg(vol + o00 + c); f01 = (float)__ldg(vol + o01 + c);
-                    f10 = (float)__ldg(vol + o10 + c); f11 = (float)__ldg(vol + o11 + c);
+            if (ks.vec4[k]) {
+                // wide float32 maps (the 1024-channel descriptors): one 128-bit load per corner and lane
+                const float* vol = static_cast<const float*>(ks.data[k]);
+                for (int c = lane * 4; c < C; c += 128) {
+                    float4 f00 = __ldg(reinterpret_cast<const float4*>(vol + o00 + c));
+                    float4 f01 = __ldg(reinterpret_cast<const float4*>(vol + o01 + c));
+                    float4 f10 = __ldg(reinterpret_cast<const float4*>(vol + o10 + c));
+                    float4 f11 = __ldg(reinterpret_cast<const float4*>(vol + o11 + c));
+                    const float4 gc = __ldg(reinterpret_cast<const float4*>(g + c));
+#define D3F_BWD_LANE(m)                                                                                     \
+                    {                                                                                       \
+                        const float a = f00.m * m00, b = f01.m * m01, cc = f10.m * m10, d2 = f11.m * m11;   \
+                        s_ix = fmaf(gc.m, (b - a) * ey + (d2 - cc) * wy, s_ix);                             \
+                        s_iy = fmaf(gc.m, (cc - a) * ex + (d2 - b) * wx, s_iy);                             \
+                        s_r = fmaf(gc.m, (a * ex + b * wx) * ey + (cc * ex + d2 * wx) * wy, s_r);           \
+                    }
+                    D3F_BWD_LANE(x) D3F_BWD_LANE(y) D3F_BWD_LANE(z) D3F_BWD_LANE(w)
+#undef D3F_BWD_LANE
                 }
-                f00 *= m00; f01 *= m01; f10 *= m10; f11 *= m11;
-                const float gc = __ldg(g + c);
-                s_ix = fmaf(gc, (f01 - f00) * (1.f - wy) + (f11 - f10) * wy, s_ix);
-                s_iy = fmaf(gc, (f10 - f00) * (1.f - wx) + (f11 - f01) * wx, s_iy);
-                s_r = fmaf(gc, (f00 * (1.f - wx) + f01 * wx) * (1.f - wy) + (f10 * (1.f - wx) + f11 * wx) * wy, s_r);
+            } else {
+                for (int c = lane; c < C; c += 32) {
+                    float f00, f01, f10, f11;
+                    if (ks.dtype[k] == D3F_F32) {
+                        const float* vol = static_cast<const float*>(ks.data[k]);
+                        f00 = __ldg(vol + o00 + c); f01 = __ldg(vol + o01 + c); f10 = __ldg(vol + o10 + c); f11 = __ldg(vol + o11 + c);
+                    } else {
+                        const uint8_t* vol = static_cast<const uint8_t*>(ks.data[k]);
+                        f00 = (float)__ldg(vol + o00 + c); f01 = (float)__ldg(vol + o01 + c);
+                        f10 = (float)__ldg(vol + o10 + c); f11 = (float)__ldg(vol + o11 + c);
+                    }
+                    f00 *= m00; f01 *= m01; f10 *= m10; f11 *= m11;
+                    const float gc = __ldg(g + c);
+                    s_ix = fmaf(gc, (f01 - f00) * ey + (f11 - f10) * wy, s_ix);
+                    s_iy = fmaf(gc, (f10 - f00) * ex + (f11 - f01) * wx, s_iy);
+                    s_r = fmaf(gc, (f00 * ex + f01 * wx) * ey + (f10 * ex + f11 * wx) * wy, s_r);
+                }
             }
 #pragma unroll
             for (int sh = 16; sh > 0; sh >>= 1) {

@@ -13,6 +13,20 @@
 
 namespace d3f {
 
+// In-kernel all-gather of the compact field (d3f_eval_allgather): where every peer's gathered arrays and
+// epoch flags live.  world == 0 means a single-GPU launch (dist / valid go to EvalParams::dist / valid).
+struct GatherParams {
+    float* dist[D3F_MAX_PEERS];          // gathered dist array in rank r's segment (r == own rank: local memory)
+    uint8_t* valid[D3F_MAX_PEERS];       // gathered valid_mask array in rank r's segment
+    uint32_t* flag[D3F_MAX_PEERS];       // &epoch_flags[own rank] in rank r's segment
+    const uint32_t* my_flags;            // epoch_flags[world] of the own segment, written by the peers
+    uint32_t* counter;                   // CTAs of this launch that have finished (own segment)
+    uint32_t* error;                     // set to 1 when a wait times out (own segment)
+    int64_t base, block, stride;         // local point i -> gathered index base + (i / block) * stride + i % block
+    uint32_t epoch;
+    int32_t world;
+};
+
 // Per-launch constants, passed by value (lives in the kernel parameter / constant bank).
 struct EvalParams {
     const float* __restrict__ pts;      // (n,3)
@@ -25,15 +39,79 @@ struct EvalParams {
     int32_t V, H, W;
     float mu;
     uint32_t flags;
+    const int32_t* __restrict__ order;  // nullptr, or (n): step i evaluates point order[i] and writes row order[i]
+    GatherParams g;
 };
 
 struct KeyParams {
-    const void* __restrict__ data;      // (V,h,w,C)
+    const void* __restrict__ data;      // (V,h,w,C), channel stride 1
     float* __restrict__ out;            // (n,C)
     float* __restrict__ inter;          // (V,n,C) or nullptr
     const float* __restrict__ bias;     // nullptr, or (C): subtracted from every output row (narrow keys only)
+    int64_t sv;                         // element stride between views
+    int32_t sy, sx;                     // element strides between rows / texels (a view spans < 2^31 elements)
     int32_t h, w, C;
 };
+
+// ---- system-scope flag traffic for the in-kernel gather -------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long COMM_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;   // a peer that is 20 s late is gone
+
+// Spin until *flag has reached `epoch` (epochs only grow; a peer may already be one ahead).  Returns false on timeout.
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch) {
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (globaltimer_ns() - t0 > COMM_TIMEOUT_NS) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
+
+// dist / valid_mask of point i of this launch: to the caller's arrays, or — gathering — into the gathered arrays of
+// every rank (remote stores over NVLink; 5 B/point/peer).
+__device__ __forceinline__ void store_compact(const EvalParams& ep, int64_t i, float dist, uint8_t valid) {
+    if (ep.g.world == 0) {
+        ep.dist[i] = dist;
+        ep.valid[i] = valid;
+        return;
+    }
+    const int64_t q = i / ep.g.block;
+    const int64_t gi = ep.g.base + q * ep.g.stride + (i - q * ep.g.block);
+    for (int r = 0; r < ep.g.world; ++r) {
+        ep.g.dist[r][gi] = dist;
+        ep.g.valid[r][gi] = valid;
+    }
+}
+
+// End of a gathering launch, called by every thread of every CTA.  The CTA's remote stores are ordered before its
+// arrival (bar.sync, then fence.sys by thread 0: cumulative); the last CTA to arrive publishes this rank's epoch to
+// every peer and waits until every peer has published the same epoch, so when the launch completes the local
+// gathered arrays hold all ranks' results.
+__device__ __forceinline__ void gather_epilogue(const EvalParams& ep) {
+    if (ep.g.world == 0) return;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    const unsigned arrived = atomicAdd(ep.g.counter, 1u);
+    if (arrived != gridDim.x - 1) return;
+    *ep.g.counter = 0;                               // the next launch on this stream starts from zero
+    __threadfence_system();
+    for (int r = 0; r < ep.g.world; ++r) st_release_sys(ep.g.flag[r], ep.g.epoch);
+    for (int r = 0; r < ep.g.world; ++r)
+        if (!wait_flag(ep.g.my_flags + r, ep.g.epoch)) { *ep.g.error = 1u; return; }
+}
 
 // Row i of H = [K@Rt ; 0 0 0 1] for one view (reference fusion.py:45-48): the small-matrix
 // product accumulates k = 0,1,2 sequentially from 0 with separate multiply and add.
@@ -116,8 +194,8 @@ __device__ __forceinline__ ViewSample view_sample(const float Hm[12], float x, f
 // clamped (always loadable) address.
 struct Footprint {
     float w[4];       // corner weights
-    int32_t off;      // texel offset of the (clamped) north-west corner: y0c*w + x0c
-    int32_t dx, dy;   // texel steps to the east / south corners after clamping (0 or 1 / 0 or w)
+    int32_t x0, y0;   // (clamped) north-west corner texel
+    int32_t dx, dy;   // 1 when the east / south corner is a different texel after clamping, else 0
 };
 
 template <bool RECIP>
@@ -139,9 +217,9 @@ __device__ __forceinline__ Footprint footprint(float px, float py, int H, int W,
     // clamp in float first: NaN and |x| >= 2^31 must not reach the int conversion
     int x0c = (int)fminf(fmaxf(x0, 0.f), xm), x1c = (int)fminf(fmaxf(x1, 0.f), xm);
     int y0c = (int)fminf(fmaxf(y0, 0.f), ym), y1c = (int)fminf(fmaxf(y1, 0.f), ym);
-    f.off = y0c * w + x0c;
+    f.x0 = x0c; f.y0 = y0c;
     f.dx = x1c - x0c;
-    f.dy = (y1c - y0c) * w;
+    f.dy = y1c - y0c;
     return f;
 }
 

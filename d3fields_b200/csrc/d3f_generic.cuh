@@ -54,21 +54,23 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& f) {
 template <typename T, int VEC, bool INTER>
 __device__ __forceinline__ void generic_accumulate(const KeyParams& kp, int V, int64_t n, int64_t tile0, int npts,
                                                    const float* s_fac, const float* s_fw,
-                                                   const int* s_off, const int* s_dx, const int* s_dy) {
+                                                   const int* s_off, const int* s_dx, const int* s_dy,
+                                                   const int32_t* __restrict__ order) {
     const int C = kp.C;
     const int G = C / VEC;
     const T* __restrict__ vol = static_cast<const T*>(kp.data);
-    const size_t view_stride = (size_t)kp.h * kp.w * C;
+    const size_t view_stride = (size_t)kp.sv;
     for (int item = threadIdx.x; item < npts * G; item += GEN_THREADS) {
         const int p = item / G;
         const int c = (item - p * G) * VEC;
+        const int64_t row = order ? (int64_t)__ldg(order + tile0 + p) : tile0 + p;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int v = 0; v < V; ++v) {
             const int s = p * V + v;
             const float fac = s_fac[s];
             if (!INTER && fac == 0.f) continue;          // invisible view: contributes exactly 0 (finite maps)
-            const T* base = vol + v * view_stride + (size_t)s_off[s] * C + c;
-            const int dx = s_dx[s] * C, dy = s_dy[s] * C;
+            const T* base = vol + v * view_stride + (size_t)s_off[s] + c;
+            const int dx = s_dx[s], dy = s_dy[s];
             const float w0 = s_fw[s * 4 + 0], w1 = s_fw[s * 4 + 1], w2 = s_fw[s * 4 + 2], w3 = s_fw[s * 4 + 3];
             if (VEC == 4) {
                 float4 f0 = Load4<T>::ld(base), f1 = Load4<T>::ld(base + dx);
@@ -80,7 +82,7 @@ __device__ __forceinline__ void generic_accumulate(const KeyParams& kp, int V, i
                     r.y = f0.y * w0 + f1.y * w1 + f2.y * w2 + f3.y * w3;
                     r.z = f0.z * w0 + f1.z * w1 + f2.z * w2 + f3.z * w3;
                     r.w = f0.w * w0 + f1.w * w1 + f2.w * w2 + f3.w * w3;
-                    if (kp.inter) __stcs(reinterpret_cast<float4*>(kp.inter + ((size_t)v * n + tile0 + p) * C + c), r);
+                    if (kp.inter) __stcs(reinterpret_cast<float4*>(kp.inter + ((size_t)v * n + row) * C + c), r);
                     fma4(acc, fac, r);
                 } else {
                     fma4(acc, w0 * fac, f0); fma4(acc, w1 * fac, f1);
@@ -90,7 +92,7 @@ __device__ __forceinline__ void generic_accumulate(const KeyParams& kp, int V, i
                 float f0 = Load4<T>::ld1(base), f1 = Load4<T>::ld1(base + dx);
                 float f2 = Load4<T>::ld1(base + dy), f3 = Load4<T>::ld1(base + dy + dx);
                 float r = f0 * w0 + f1 * w1 + f2 * w2 + f3 * w3;
-                if (INTER && kp.inter) __stcs(kp.inter + ((size_t)v * n + tile0 + p) * C + c, r);
+                if (INTER && kp.inter) __stcs(kp.inter + ((size_t)v * n + row) * C + c, r);
                 acc.x = fmaf(fac, r, acc.x);
             }
         }
@@ -102,7 +104,7 @@ __device__ __forceinline__ void generic_accumulate(const KeyParams& kp, int V, i
                 acc.x -= __ldg(kp.bias + c);
             }
         }
-        float* o = kp.out + (size_t)(tile0 + p) * C + c;
+        float* o = kp.out + (size_t)row * C + c;
         if (VEC == 4) __stcs(reinterpret_cast<float4*>(o), acc);
         else          __stcs(o, acc.x);
     }
@@ -141,7 +143,8 @@ field_generic_kernel(const EvalParams ep, const KeySet ks) {
     // phase 1: slot s = p*V + v, threads view-major so a warp walks consecutive points of one view
     for (int item = threadIdx.x; item < npts * V; item += GEN_THREADS) {
         const int v = item / npts, p = item - v * npts;
-        const float* q = ep.pts + (size_t)(tile0 + p) * 3;
+        const int64_t row = ep.order ? (int64_t)__ldg(ep.order + tile0 + p) : tile0 + p;
+        const float* q = ep.pts + (size_t)row * 3;
         const float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
         float Hm[12];
 #pragma unroll
@@ -165,15 +168,17 @@ field_generic_kernel(const EvalParams ep, const KeySet ks) {
         const float denom = __fadd_rn(cnt, 1e-6f);
         float dist = __fdiv_rn(acc, denom);
         if (!eval_dist && cnt == 0.f) dist = 1e3f;                            // fusion.py:367
-        ep.dist[tile0 + p] = dist;
-        ep.valid[tile0 + p] = cnt != 0.f ? 1 : 0;
+        store_compact(ep, ep.order ? (int64_t)__ldg(ep.order + tile0 + p) : tile0 + p, dist, cnt != 0.f ? 1 : 0);
         const float inv = __fdiv_rn(1.f, denom);
         for (int v = 0; v < V; ++v) {
             const int s = p * V + v;
             s_fac[s] = s_vis[s] ? __fmul_rn(s_fac[s], inv) : 0.f;             // weight/(count+1e-6), fusion.py:385
         }
     }
-    if (eval_dist || ks.n_keys == 0) return;
+    if (eval_dist || ks.n_keys == 0) {
+        gather_epilogue(ep);
+        return;
+    }
     __syncthreads();
 
     for (int k = 0; k < ks.n_keys; ++k) {
@@ -181,19 +186,21 @@ field_generic_kernel(const EvalParams ep, const KeySet ks) {
         for (int s = threadIdx.x; s < npts * V; s += GEN_THREADS) {
             Footprint f = footprint<RECIP>(s_px[s], s_py[s], ep.H, ep.W, kp.h, kp.w);
             s_fw[s * 4 + 0] = f.w[0]; s_fw[s * 4 + 1] = f.w[1]; s_fw[s * 4 + 2] = f.w[2]; s_fw[s * 4 + 3] = f.w[3];
-            s_off[s] = f.off; s_dx[s] = f.dx; s_dy[s] = f.dy;
+            s_off[s] = f.y0 * kp.sy + f.x0 * kp.sx;
+            s_dx[s] = f.dx ? kp.sx : 0; s_dy[s] = f.dy ? kp.sy : 0;
         }
         __syncthreads();
-        const bool vec4 = (kp.C % 4 == 0);
+        const bool vec4 = (kp.C % 4 == 0) && ((kp.sv | kp.sy | kp.sx) & 3) == 0;
         if (ks.dtype[k] == D3F_F32) {
-            if (vec4) generic_accumulate<float, 4, INTER>(kp, V, ep.n, tile0, npts, s_fac, s_fw, s_off, s_dx, s_dy);
-            else      generic_accumulate<float, 1, INTER>(kp, V, ep.n, tile0, npts, s_fac, s_fw, s_off, s_dx, s_dy);
+            if (vec4) generic_accumulate<float, 4, INTER>(kp, V, ep.n, tile0, npts, s_fac, s_fw, s_off, s_dx, s_dy, ep.order);
+            else      generic_accumulate<float, 1, INTER>(kp, V, ep.n, tile0, npts, s_fac, s_fw, s_off, s_dx, s_dy, ep.order);
         } else {
-            if (vec4) generic_accumulate<uint8_t, 4, INTER>(kp, V, ep.n, tile0, npts, s_fac, s_fw, s_off, s_dx, s_dy);
-            else      generic_accumulate<uint8_t, 1, INTER>(kp, V, ep.n, tile0, npts, s_fac, s_fw, s_off, s_dx, s_dy);
+            if (vec4) generic_accumulate<uint8_t, 4, INTER>(kp, V, ep.n, tile0, npts, s_fac, s_fw, s_off, s_dx, s_dy, ep.order);
+            else      generic_accumulate<uint8_t, 1, INTER>(kp, V, ep.n, tile0, npts, s_fac, s_fw, s_off, s_dx, s_dy, ep.order);
         }
         __syncthreads();
     }
+    gather_epilogue(ep);
 }
 
 }  // namespace d3f

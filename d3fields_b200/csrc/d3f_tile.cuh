@@ -42,7 +42,10 @@ struct TileSmem {
     float fac[TILE_PTS * TILE_V];
     int vis[TILE_PTS * TILE_V];
     float4 w4[TILE_PTS * TILE_V];     // folded corner weights per (point, view)
-    int4 code[TILE_PTS + 4];          // packed footprint codes of the 4 views of a point
+    int4 code[TILE_PTS + 4];          // packed footprint codes of the 4 views of a point: element offset of the
+                                      // north-west texel inside the view (wide maps: a multiple of 4, used as is;
+                                      // narrow maps: shifted left by 2) | east-step bit | south-step bit << 1; -1 = unseen
+    int64_t row[TILE_PTS];            // output row of each point of the tile (ordered launches only)
     int mask[TILE_PTS + 4];           // bits 0-3: view sees the point; bits 4-7: its corner cell differs from
                                       // the previous point's (or the previous point did not see it);
                                       // bits 12-15: bits 4-7 of the point WIDE_LOOKAHEAD further on in the same run
@@ -65,9 +68,9 @@ __host__ __device__ inline int wide_run_len(int S) { const int R = wide_runs(S);
 // 32-bit element offsets: a view's map holds fewer than 2^31 elements (checked on the host).
 #define D3F_WIDE_RELOAD(v, cv)                                                                     \
     {                                                                                              \
-        const float* b_ = vbase[v] + (unsigned)((cv) >> 2) * (unsigned)C;                          \
-        const unsigned dx_ = ((cv) & 1) ? (unsigned)C : 0u;                                        \
-        const unsigned dy_ = ((cv) & 2) ? (unsigned)rowC : 0u;                                     \
+        const float* b_ = vbase[v] + (unsigned)((cv) & ~3);                                        \
+        const unsigned dx_ = ((cv) & 1) ? (unsigned)kp.sx : 0u;                                    \
+        const unsigned dy_ = ((cv) & 2) ? (unsigned)kp.sy : 0u;                                    \
         cc[v][0] = ldg4(b_); cc[v][1] = ldg4(b_ + dx_);                                            \
         cc[v][2] = ldg4(b_ + dy_); cc[v][3] = ldg4(b_ + (dy_ + dx_));                              \
     }
@@ -82,7 +85,7 @@ constexpr int WIDE_LOOKAHEAD = 4;      // points between the L1 prefetch of a ce
 // PREFETCH: bits 12-15 of a point's mask word say which views change cell WIDE_LOOKAHEAD points later; the warp
 // then prefetches its own 512-byte slice of those corner texels into L1, so the reload that follows is an L1 hit
 // instead of an L2 round trip with all eight warps of the CTA stalled on the same point.
-template <bool PREFETCH>
+template <bool PREFETCH, bool ORDERED>
 __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmem& sm) {
     const int C = kp.C;
     const int S = C >> 7;                                   // 128-channel slices
@@ -100,13 +103,12 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
     }
     if (p_end <= p_begin) return;
     const float* __restrict__ vol = static_cast<const float*>(kp.data);
-    const size_t vstride = (size_t)kp.h * kp.w * C;
-    const int rowC = kp.w * C;
     for (int s = s0; s < S; s += sstep) {
         const float* vbase[TILE_V];
 #pragma unroll
-        for (int v = 0; v < TILE_V; ++v) vbase[v] = vol + (size_t)v * vstride + s * 128 + lane * 4;
+        for (int v = 0; v < TILE_V; ++v) vbase[v] = vol + (size_t)v * (size_t)kp.sv + s * 128 + lane * 4;
         float* o = kp.out + (size_t)(tile0 + p_begin) * C + s * 128 + lane * 4;
+        float* const o_col = kp.out + s * 128 + lane * 4;
         float4 cc[TILE_V][4];
 #pragma unroll
         for (int v = 0; v < TILE_V; ++v)
@@ -125,9 +127,9 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
                 for (int v = 0; v < TILE_V; ++v) {
                     if (m & (0x1000u << v)) {
                         const int cv = cvs[v];
-                        const float* b_ = vbase[v] + (unsigned)(cv >> 2) * (unsigned)C;
-                        const unsigned dx_ = (cv & 1) ? (unsigned)C : 0u;
-                        const unsigned dy_ = (cv & 2) ? (unsigned)rowC : 0u;
+                        const float* b_ = vbase[v] + (unsigned)(cv & ~3);
+                        const unsigned dx_ = (cv & 1) ? (unsigned)kp.sx : 0u;
+                        const unsigned dy_ = (cv & 2) ? (unsigned)kp.sy : 0u;
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(b_));
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(b_ + dx_));
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(b_ + dy_));
@@ -155,18 +157,17 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
                 if (m & 4u) D3F_WIDE_FMA(2, w2)
                 if (m & 8u) D3F_WIDE_FMA(3, w3)
             }
-            __stcs(reinterpret_cast<float4*>(o), acc);
+            if (ORDERED) __stcs(reinterpret_cast<float4*>(o_col + (size_t)sm.row[p] * C), acc);
+            else         __stcs(reinterpret_cast<float4*>(o), acc);
         }
     }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool ORDERED>
 __device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmem& sm) {
     const int C = kp.C;
     const int G = C / VEC;
     const T* __restrict__ vol = static_cast<const T*>(kp.data);
-    const size_t vstride = (size_t)kp.h * kp.w * C;
-    const int rowC = kp.w * C;
     const int* codes = reinterpret_cast<const int*>(sm.code);
     for (int item = threadIdx.x; item < npts * G; item += TILE_THREADS) {
         const int p = item / G;
@@ -176,8 +177,8 @@ __device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t t
         for (int v = 0; v < TILE_V; ++v) {
             const int cv = codes[p * TILE_V + v];
             if (cv < 0) continue;
-            const T* b = vol + (size_t)v * vstride + (size_t)(cv >> 2) * (size_t)C + c;
-            const int dx = (cv & 1) ? C : 0, dy = (cv & 2) ? rowC : 0;
+            const T* b = vol + (size_t)v * (size_t)kp.sv + (size_t)(cv >> 2) + c;
+            const int dx = (cv & 1) ? kp.sx : 0, dy = (cv & 2) ? kp.sy : 0;
             const float4 w = sm.w4[p * TILE_V + v];
             if (VEC == 4) {
                 fma4(acc, w.x, Load4<T>::ld(b)); fma4(acc, w.y, Load4<T>::ld(b + dx));
@@ -195,21 +196,29 @@ __device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t t
                 acc.x -= __ldg(kp.bias + c);
             }
         }
-        float* o = kp.out + (size_t)(tile0 + p) * C + c;
+        float* o = kp.out + (size_t)(ORDERED ? sm.row[p] : tile0 + p) * C + c;
         if (VEC == 4) __stcs(reinterpret_cast<float4*>(o), acc);
         else          __stcs(o, acc.x);
     }
 }
 
+// Elements spanned by one view of a key (strided): the packed footprint codes hold offsets below this.
+__host__ __device__ inline long long key_extent(int h, int w, int C, long long sy, long long sx) {
+    return (long long)(h - 1) * sy + (long long)(w - 1) * sx + C;
+}
 // wide-path eligibility of one key (host and device agree through this one function)
-__host__ __device__ inline bool key_is_wide(int dtype, int C, int h, int w) {
-    return dtype == D3F_F32 && (C % 128) == 0 && (long long)h * w < (1ll << 29) && (long long)h * w * C < (1ll << 31);
+__host__ __device__ inline bool key_is_wide(int dtype, int C, int h, int w, long long sv, long long sy, long long sx) {
+    return dtype == D3F_F32 && (C % 128) == 0 && ((sv | sy | sx) & 3) == 0 && key_extent(h, w, C, sy, sx) < (1ll << 31);
+}
+// the tile kernel's narrow path packs (offset << 2 | step bits) into 31 bits
+__host__ __device__ inline bool key_fits_tile(int dtype, int C, int h, int w, long long sv, long long sy, long long sx) {
+    return key_is_wide(dtype, C, h, w, sv, sy, sx) || key_extent(h, w, C, sy, sx) < (1ll << 29);
 }
 
 // WIDE=false compiles the register-cached walk out: launches with only narrow keys (instance masks, colours,
 // PCA-projected volumes) or no keys at all (dist / valid_mask sweeps) then need ~60 registers and run 4 CTAs
 // per SM instead of 2.
-template <bool RECIP, int VARIANT, bool WIDE>
+template <bool RECIP, int VARIANT, bool WIDE, bool ORDERED>
 __global__ void __launch_bounds__(TILE_THREADS, WIDE ? 2 : 4)
 field_tile_kernel(const EvalParams ep, const KeySet ks) {
     __shared__ TileSmem sm;
@@ -231,7 +240,12 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
     for (int item = threadIdx.x; item < TILE_PTS * V; item += TILE_THREADS) {
         const int v = item / TILE_PTS, p = item - v * TILE_PTS;
         if (p >= npts) continue;
-        const float* q = ep.pts + (size_t)(tile0 + p) * 3;
+        int64_t row = tile0 + p;
+        if (ORDERED) {
+            row = __ldg(ep.order + tile0 + p);
+            if (v == 0) sm.row[p] = row;
+        }
+        const float* q = ep.pts + (size_t)row * 3;
         const float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
         float Hm[12];
 #pragma unroll
@@ -254,20 +268,23 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
         const float denom = __fadd_rn(cnt, 1e-6f);
         float dist = __fdiv_rn(acc, denom);
         if (!eval_dist && cnt == 0.f) dist = 1e3f;                           // fusion.py:367
-        ep.dist[tile0 + p] = dist;
-        ep.valid[tile0 + p] = cnt != 0.f ? 1 : 0;
+        store_compact(ep, ORDERED ? sm.row[p] : tile0 + p, dist, cnt != 0.f ? 1 : 0);
         const float inv = __fdiv_rn(1.f, denom);
         for (int v = 0; v < V; ++v) {
             const int s = p * TILE_V + v;
             sm.fac[s] = sm.vis[s] ? __fmul_rn(sm.fac[s], inv) : 0.f;          // weight/(count+1e-6), fusion.py:385
         }
     }
-    if (eval_dist || ks.n_keys == 0) return;
+    if (eval_dist || ks.n_keys == 0) {
+        gather_epilogue(ep);
+        return;
+    }
     __syncthreads();
 
     int* codes = reinterpret_cast<int*>(sm.code);
     for (int k = 0; k < ks.n_keys; ++k) {
         const KeyParams& kp = ks.k[k];
+        const bool wide = WIDE && key_is_wide(ks.dtype[k], kp.C, kp.h, kp.w, kp.sv, kp.sy, kp.sx);
         for (int s = threadIdx.x; s < TILE_PTS * TILE_V; s += TILE_THREADS) {
             const int p = s >> 2, v = s & 3;
             int code = -1;
@@ -275,12 +292,13 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
                 const Footprint f = footprint<RECIP>(sm.px[s], sm.py[s], ep.H, ep.W, kp.h, kp.w);
                 const float fac = sm.fac[s];
                 sm.w4[s] = make_float4(f.w[0] * fac, f.w[1] * fac, f.w[2] * fac, f.w[3] * fac);
-                code = (f.off << 2) | (f.dx ? 1 : 0) | (f.dy ? 2 : 0);
+                const int eo = f.y0 * kp.sy + f.x0 * kp.sx;
+                code = (wide ? eo : (eo << 2)) | (f.dx ? 1 : 0) | (f.dy ? 2 : 0);
             }
             codes[s] = code;
         }
         __syncthreads();
-        if (WIDE && key_is_wide(ks.dtype[k], kp.C, kp.h, kp.w)) {
+        if (wide) {
             // per-point mask: which views see the point, and which of those changed texel cell since the
             // previous point of the same run (a view the previous point did not see always reloads)
             if (threadIdx.x < TILE_PTS) {
@@ -312,19 +330,20 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
                 if (threadIdx.x < TILE_PTS) sm.mask[threadIdx.x] |= ahead;
             }
             __syncthreads();
-            wide_accumulate<(VARIANT & 4) != 0>(kp, tile0, npts, sm);
+            wide_accumulate<(VARIANT & 4) != 0, ORDERED>(kp, tile0, npts, sm);
         } else {
-            const bool vec4 = (kp.C % 4 == 0);
+            const bool vec4 = (kp.C % 4 == 0) && ((kp.sv | kp.sy | kp.sx) & 3) == 0;
             if (ks.dtype[k] == D3F_F32) {
-                if (vec4) narrow_accumulate<float, 4>(kp, tile0, npts, sm);
-                else      narrow_accumulate<float, 1>(kp, tile0, npts, sm);
+                if (vec4) narrow_accumulate<float, 4, ORDERED>(kp, tile0, npts, sm);
+                else      narrow_accumulate<float, 1, ORDERED>(kp, tile0, npts, sm);
             } else {
-                if (vec4) narrow_accumulate<uint8_t, 4>(kp, tile0, npts, sm);
-                else      narrow_accumulate<uint8_t, 1>(kp, tile0, npts, sm);
+                if (vec4) narrow_accumulate<uint8_t, 4, ORDERED>(kp, tile0, npts, sm);
+                else      narrow_accumulate<uint8_t, 1, ORDERED>(kp, tile0, npts, sm);
             }
         }
         __syncthreads();
     }
+    gather_epilogue(ep);
 }
 
 }  // namespace d3f

@@ -75,7 +75,8 @@ class _FieldQuery(torch.autograd.Function):
             if vol.dtype == torch.bool:
                 vol = vol.view(torch.uint8)
             dt = _native.D3F_F32 if vol.dtype == torch.float32 else _native.D3F_U8
-            keys.append((vol.data_ptr(), dt, int(vol.shape[1]), int(vol.shape[2]), int(vol.shape[3])))
+            strides = None if vol.is_contiguous() else tuple(int(x) for x in vol.stride()[:3])
+            keys.append((vol.data_ptr(), dt, int(vol.shape[1]), int(vol.shape[2]), int(vol.shape[3]), None, strides))
             grads.append(None if g is None else g.contiguous().float())
         gd = None if g_dist is None else g_dist.contiguous().float()
         grad_pts = torch.empty_like(pts)
@@ -225,10 +226,19 @@ class Fusion:
             vol = vol.view(torch.uint8)
         if vol.dtype not in (torch.float32, torch.uint8):
             raise ValueError(f"curr_obs_torch['{name}'] must be float32 or uint8, got {vol.dtype}")
-        if not (vol.is_cuda and vol.is_contiguous()):
-            raise ValueError(f"curr_obs_torch['{name}'] must be a contiguous CUDA tensor (channels-last (V,h,w,C))")
+        if not vol.is_cuda:
+            raise ValueError(f"curr_obs_torch['{name}'] must be a CUDA tensor")
         dt = _native.D3F_F32 if vol.dtype == torch.float32 else _native.D3F_U8
-        return (vol.data_ptr(), dt, int(vol.shape[1]), int(vol.shape[2]), int(vol.shape[3])), vol
+        strides = None
+        if not vol.is_contiguous():
+            # a crop / padded map / permuted view is sampled in place through D3FKey's strides (the reference samples
+            # a permuted view of its tensor too, fusion.py:373); only the channel axis must be dense
+            sv, sy, sx, sc = (int(x) for x in vol.stride())
+            if (sc != 1 and vol.shape[3] != 1) or min(sv, sy, sx) < 0:
+                raise ValueError(f"curr_obs_torch['{name}'] must be channels-last (V,h,w,C) with unit channel stride; "
+                                 f'got strides {tuple(vol.stride())}')
+            strides = (sv, sy, sx)
+        return (vol.data_ptr(), dt, int(vol.shape[1]), int(vol.shape[2]), int(vol.shape[3]), None, strides), vol
 
     def _flags(self, eval_dist=False):
         f = _native.FLAG_EVAL_DIST if eval_dist else 0
@@ -238,7 +248,27 @@ class Fusion:
             raise ValueError("index_rounding must be 'cpu' or 'cuda'")
         return f
 
-    def _run(self, pts, return_names, return_inter, eval_dist, out=None):
+    def bin_order(self, pts, cell=None):
+        """Visiting order (int32 permutation, device) that groups `pts` (n,3) by lattice cell in Morton order
+        (d3f_bin_order) — for keypoints / mesh vertices, which arrive without the z-fastest locality of a
+        create_init_grid grid.  `cell` defaults to ~1/128 of the cloud's extent, at least 2.5 mm."""
+        n = int(pts.shape[0])
+        dev = pts.device
+        with torch.cuda.device(dev):
+            order = torch.empty(n, dtype=torch.int32, device=dev)
+            if n == 0:
+                return order
+            if cell is None:
+                cell = 0.0025
+            nbytes = _native.bin_workspace_bytes(n)
+            ws = getattr(self, '_bin_ws', None)
+            if ws is None or ws.numel() < nbytes or ws.device != dev:
+                ws = self._bin_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _native.bin_order(pts.data_ptr(), n, float(cell), order.data_ptr(), ws.data_ptr(), ws.numel(),
+                              torch.cuda.current_stream(dev).cuda_stream)
+        return order
+
+    def _run(self, pts, return_names, return_inter, eval_dist, out=None, binned=False, gather=None):
         self._check_pts(pts)
         names = list(return_names)
         V, H, W, pose_p, K_p, depth_p = self._obs_ptrs()
@@ -263,15 +293,34 @@ class Fusion:
                     return t
                 return torch.empty(shape, dtype=dtype, device=dev)
 
-            dist = buf('dist', (n,), torch.float32)
-            valid = buf('valid_mask', (n,), torch.bool)
             outs = [buf(k, (n, kt[4]), torch.float32) for k, kt in zip(names, keys)]
-            inters = [torch.empty((V, n, kt[4]), dtype=torch.float32, device=dev) for kt in keys] if return_inter else None
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _native.eval_device(V, H, W, pose_p, K_p, depth_p, pts.data_ptr(), n, keys,
-                                dist.data_ptr(), valid.data_ptr(), [o.data_ptr() for o in outs],
-                                [t.data_ptr() for t in inters] if inters is not None else None,
-                                self._flags(eval_dist), float(self.mu), stream)
+            if gather is not None:
+                # in-kernel all-gather of dist / valid_mask into every rank's gathered arrays (d3f_eval_allgather)
+                if return_inter or binned:
+                    raise ValueError('a gathering launch supports neither return_inter nor binned')
+                comm, base, block, stride = gather
+                dist, valid = comm.eval_allgather(V, H, W, pose_p, K_p, depth_p, pts.data_ptr(), n, keys,
+                                                  [o.data_ptr() for o in outs], base, block, stride,
+                                                  self._flags(eval_dist), float(self.mu), stream)
+                inters = None
+            else:
+                dist = buf('dist', (n,), torch.float32)
+                valid = buf('valid_mask', (n,), torch.bool)
+                inters = [torch.empty((V, n, kt[4]), dtype=torch.float32, device=dev) for kt in keys] if return_inter else None
+                if binned is not False and binned is not None and n > 0:
+                    if return_inter:
+                        raise ValueError('binned=True does not support return_inter')
+                    order = binned if isinstance(binned, torch.Tensor) else \
+                        self.bin_order(pts, None if binned is True else float(binned))
+                    _native.eval_ordered(V, H, W, pose_p, K_p, depth_p, pts.data_ptr(), n, order.data_ptr(), keys,
+                                         dist.data_ptr(), valid.data_ptr(), [o.data_ptr() for o in outs],
+                                         self._flags(eval_dist), float(self.mu), stream)
+                else:
+                    _native.eval_device(V, H, W, pose_p, K_p, depth_p, pts.data_ptr(), n, keys,
+                                        dist.data_ptr(), valid.data_ptr(), [o.data_ptr() for o in outs],
+                                        [t.data_ptr() for t in inters] if inters is not None else None,
+                                        self._flags(eval_dist), float(self.mu), stream)
         res = {'dist': dist, 'valid_mask': valid}
         for i, k in enumerate([] if eval_dist else names):
             res[k] = outs[i]
@@ -300,17 +349,19 @@ class Fusion:
         with torch.cuda.device(dev):
             _native.eval_host(V, H, W, pose_p, K_p, depth_p, pts.data_ptr(), n, keys,
                               dist.data_ptr(), valid.data_ptr(), [o.data_ptr() for o in outs],
-                              self._flags(eval_dist), float(self.mu))
+                              self._flags(eval_dist), float(self.mu), torch.cuda.current_stream(dev).cuda_stream)
         res = {'dist': dist, 'valid_mask': valid}
         for k, o in zip(names, outs):
             res[k] = o
         return res
 
-    def eval(self, pts, return_names=['dino_feats', 'mask'], return_inter=False, out=None):
+    def eval(self, pts, return_names=['dino_feats', 'mask'], return_inter=False, out=None, binned=False):
         """(N,3) world points -> {'dist' (N,), 'valid_mask' (N,) bool, '<k>' (N,C_k) for k in return_names
         [, '<k>_inter' (V,N,C_k)]}.  Reference fusion.py:305-394.  CPU `pts` give CPU results through the
-        host-buffer entry point (return_inter is device-only).  `out` (an extension) may hold preallocated
-        tensors for 'dist' / 'valid_mask' / any name; the kernel writes them in place."""
+        host-buffer entry point (return_inter is device-only).  Extensions: `out` may hold preallocated
+        tensors for 'dist' / 'valid_mask' / any name (the kernel writes them in place); `binned=True` (or a cell
+        size in metres, or a precomputed bin_order() tensor) walks the points in lattice-cell order — same results
+        bit for bit, about twice as fast for keypoints / mesh vertices that arrive in no spatial order."""
         if isinstance(pts, torch.Tensor) and not pts.is_cuda and return_inter:
             raise ValueError('return_inter needs device points')
         if isinstance(pts, torch.Tensor) and pts.requires_grad and torch.is_grad_enabled():
@@ -322,7 +373,7 @@ class Fusion:
             res = {'dist': outs[0], 'valid_mask': outs[1]}
             res.update({k: outs[2 + i] for i, k in enumerate(names)})
             return res
-        return self._run(pts, return_names, return_inter, eval_dist=False, out=out)
+        return self._run(pts, return_names, return_inter, eval_dist=False, out=out, binned=binned)
 
     def eval_dist(self, pts):
         """Unclamped signed distance: {'dist', 'valid_mask'}.  Reference fusion.py:396-436."""
@@ -342,6 +393,76 @@ class Fusion:
         V, H, W, pose_p, K_p, depth_p = self._obs_ptrs()
         keys = [self._key_tuple(k, V)[0] for k in names]
         return self._run_host(pts, names, keys, V, H, W, pose_p, K_p, depth_p, False, out=out)
+
+    # ------------------------------------------------------------------ dense sweeps -----
+    def sweep_select(self, boundaries=None, res=0.001, pts=None, dist_threshold=0.005, mask_threshold=0.6,
+                     mask_name='mask', capacity=None, dense=False):
+        """The candidate search of select_features_rand / select_features_from_pcd (reference fusion.py:1420-1445,
+        1477-1501) as ONE fused launch: for every voxel centre of create_init_grid(boundaries, res) — or every row of
+        `pts` — dist / valid_mask, and where valid & |dist| < dist_threshold the normalised instance-mask field
+        mask / (mask.sum(1) + 1e-7); points with an instance i >= 1 above mask_threshold are stream-compacted on the
+        device.  Neither the grid (1.2 GB at the reference's 1 mm resolution) nor the dense mask field exists in HBM.
+
+        Returns {'index' (K,) int64 ascending linear point index, 'inst' (K,) int64 instance id,
+                 'pts' (K,3) the selected points, 'grid_shape' (sweeps of a grid), 'count' K
+                 [, 'dist' (N,), 'valid_mask' (N,) when dense=True — what extract_mesh consumes, fusion.py:1321]}.
+        The reference's masked_pts of instance i is  res['pts'][res['inst'] == i]  (same order)."""
+        if len(self.curr_obs_torch) == 0:
+            print('Please call update() first!')
+            exit()
+        V, H, W, pose_p, K_p, depth_p = self._obs_ptrs()
+        dev = self.curr_obs_torch['depth'].device
+        mk = None
+        if mask_name is not None:
+            kt, _vol = self._key_tuple(mask_name, V)
+            mk = kt
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            grid = None
+            if pts is None:
+                # the three axis arrays exactly as the reference builds them (fusion.py:83-85); the kernel indexes them
+                axes = [(torch.arange(boundaries[a + '_lower'], boundaries[a + '_upper'], res, dtype=torch.float32)
+                         + res / 2).to(dev) for a in ('x', 'y', 'z')]
+                shape = torch.Size(int(a.numel()) for a in axes)
+                n = int(shape[0] * shape[1] * shape[2])
+                grid = (axes[0].data_ptr(), axes[1].data_ptr(), axes[2].data_ptr(), shape[0], shape[1], shape[2])
+                pts_p = None
+            else:
+                self._check_pts(pts)
+                if not pts.is_cuda or pts.device != dev:
+                    raise ValueError(f'pts must be on {dev}')
+                pts = pts.contiguous()
+                n, pts_p, shape, axes = int(pts.shape[0]), pts.data_ptr(), None, None
+            dist = torch.empty(n, dtype=torch.float32, device=dev) if dense else None
+            valid = torch.empty(n, dtype=torch.bool, device=dev) if dense else None
+            cap = int(capacity) if capacity is not None else max(min(n, 1 << 16), n // 16)
+            while True:
+                count = torch.zeros(1, dtype=torch.int64, device=dev)
+                sel_i = torch.empty(cap, dtype=torch.int32, device=dev)
+                sel_c = torch.empty(cap, dtype=torch.int32, device=dev)
+                _native.sweep_select(V, H, W, pose_p, K_p, depth_p, grid, pts_p, n, mk, float(dist_threshold),
+                                     float(mask_threshold), None if dist is None else dist.data_ptr(),
+                                     None if valid is None else valid.data_ptr(), cap if mk is not None else 0,
+                                     count.data_ptr() if mk is not None else None,
+                                     sel_i.data_ptr() if mk is not None else None,
+                                     sel_c.data_ptr() if mk is not None else None, self._flags(False), float(self.mu), stream)
+                k = int(count.item()) if mk is not None else 0
+                if k <= cap:
+                    break
+                cap = k                                        # rare: the shell held more points than guessed
+            idx, perm = torch.sort(sel_i[:k].long())
+            inst = sel_c[:k].long()[perm]
+            if pts is None:
+                nz, ny = shape[2], shape[1]
+                sel_pts = torch.stack([axes[0][idx // (ny * nz)], axes[1][(idx // nz) % ny], axes[2][idx % nz]], -1)
+            else:
+                sel_pts = pts[idx]
+        res_d = {'index': idx, 'inst': inst, 'pts': sel_pts, 'count': k}
+        if shape is not None:
+            res_d['grid_shape'] = shape
+        if dense:
+            res_d['dist'], res_d['valid_mask'] = dist, valid
+        return res_d
 
     def eval_pca(self, pts, name, mean, components):
         """eval(pts, [name])[name] followed by sklearn's PCA.transform, (row - mean) @ components.T (what the

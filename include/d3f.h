@@ -30,9 +30,11 @@
 extern "C" {
 #endif
 
-#define D3F_ABI_VERSION 1
+#define D3F_ABI_VERSION 2
 #define D3F_MAX_VIEWS 16
 #define D3F_MAX_KEYS 8
+#define D3F_MAX_PEERS 8            /* GPUs of one box that can share a gather (d3f_comm_*) */
+#define D3F_IPC_HANDLE_BYTES 64    /* sizeof(cudaIpcMemHandle_t) */
 
 /* element type of a sampled map */
 #define D3F_F32 0
@@ -50,6 +52,7 @@ extern "C" {
 #define D3F_EINVAL       -1   /* bad argument (null pointer, V/C/n out of range, unknown dtype) */
 #define D3F_ECUDA        -2   /* a CUDA runtime call failed; see d3f_last_error() */
 #define D3F_EUNSUPPORTED -3   /* the device is not sm_100 */
+#define D3F_ETIMEOUT     -4   /* a peer never signalled (d3f_comm_status) */
 
 /* The per-frame observation: Fusion.curr_obs_torch['pose'|'K'|'depth'] + Fusion.H/W
  * (reference fusion.py:710-714). */
@@ -67,6 +70,12 @@ typedef struct D3FKey {
     const void* data;     /* (V,h,w,C) channels-last, contiguous */
     int32_t dtype;        /* D3F_F32 | D3F_U8 */
     int32_t h, w, C;
+    int64_t stride_v, stride_y, stride_x;
+                          /* element strides of the view / row / texel axes; all three 0 = contiguous
+                             (h*w*C, w*C, C).  The channel axis always has stride 1 (what makes the gather
+                             coalesced).  Lets a caller pass a crop or a padded map without a copy: the
+                             reference samples a permuted *view* of its (V,h,w,C) tensor (fusion.py:373).
+                             When C % 4 == 0 every stride must be a multiple of 4 elements. */
     const float* bias;    /* NULL, or (C) device floats subtracted from every output row (C < 128 only).
                              Used for PCA'd descriptor fields: because the field is linear in the sampled map,
                              (field - mean) @ W^T == field_of(map @ W^T) - mean @ W^T, so the map is projected
@@ -99,12 +108,39 @@ int d3f_eval(const D3FObs* obs, const float* pts, int64_t n,
 /* Same computation with HOST pts / outputs (observation and maps stay device-resident, as
  * after Fusion.update()).  Points are uploaded and results downloaded in slabs, copies
  * overlapped with the kernels on internal streams; pinned host memory gives full PCIe rate.
- * This is the call bench.py's end-to-end number times.  Synchronous. */
+ * This is the call bench.py's end-to-end number times.  Synchronous: returns after the last copy
+ * has completed (also on error: no copy into the caller's buffers is left in flight).
+ * `obs_stream` is the stream the observation was last written on (the call orders itself after it
+ * with an event; no device-wide synchronisation).  Thread-safe: concurrent callers use separate
+ * scratch (streams + device slabs) from a pool that d3f_release_scratch() frees. */
 int d3f_eval_host(const D3FObs* obs, const float* pts_host, int64_t n,
                   const D3FKey* keys, int32_t n_keys,
                   float* dist_host, uint8_t* valid_host,
                   float* const* out_host,
-                  uint32_t flags, float mu);
+                  uint32_t flags, float mu, void* obs_stream);
+
+/* Free the pooled scratch of d3f_eval_host (device slabs, streams) of the current device. */
+int d3f_release_scratch(void);
+
+/* Binned traversal for query points without spatial order (keypoints, mesh vertices; the tracking
+ * use of the reference, vis_tracking.py:92-130 / fusion.py:1449,1650).  d3f_bin_order writes to
+ * `order` (n int32, device) a permutation that groups points by the cell of a cubic lattice of
+ * edge `cell` metres they fall in, cells in Morton (z-curve) order: neighbouring points of the
+ * permuted sequence project into the same texel cells of EVERY view, which is what the wide walk's
+ * register cache of corner texels needs.  `workspace` is device scratch of at least
+ * d3f_bin_workspace_bytes(n) bytes.  Asynchronous on `stream`. */
+int64_t d3f_bin_workspace_bytes(int64_t n);
+int d3f_bin_order(const float* pts, int64_t n, float cell, int32_t* order,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* d3f_eval visiting the points in the sequence order[0..n) (any permutation of 0..n-1, e.g. from
+ * d3f_bin_order): point order[i] is evaluated at step i and its results are written to row
+ * order[i], so every output is identical — bit for bit — to d3f_eval's.  out_inter is not
+ * supported here. */
+int d3f_eval_ordered(const D3FObs* obs, const float* pts, int64_t n, const int32_t* order,
+                     const D3FKey* keys, int32_t n_keys,
+                     float* dist, uint8_t* valid, float* const* out,
+                     uint32_t flags, float mu, void* stream);
 
 /* Gradient of d3f_eval's outputs with respect to the query points: what torch autograd computes when the
  * reference's rigid_tracking back-propagates through Fusion.eval (reference fusion.py:1643-1665).
@@ -133,6 +169,86 @@ int d3f_pca_project(const float* x, int64_t n, int32_t C,
 int d3f_create_grid(double x_lower, double y_lower, double z_lower, double step,
                     int32_t nx, int32_t ny, int32_t nz, float* pts, void* stream);
 
+/* Fused dense sweep: the candidate search of select_features_rand / select_features_from_pcd
+ * (reference fusion.py:1420-1445, 1477-1501) and the dense `dist` volume extract_mesh consumes
+ * (fusion.py:1321-1322) without the grid or the dense mask field ever existing in HBM.
+ *
+ * Points: voxel centres of a create_init_grid grid (fusion.py:79-88) taken from the three axis
+ * arrays (device; exactly torch.arange(lower, upper, step) + step/2 as the reference computes them,
+ * so the coordinates are the reference's bit for bit), linear index i = (ix*ny + iy)*nz + iz
+ * (z fastest) — or, when grid is NULL, the n rows of `pts`.
+ *
+ * Per point: dist / valid_mask as d3f_eval; then, only where valid && |dist| < dist_threshold,
+ * the field of the one-hot instance mask `mask_key` (u8 or f32, (V,h,w,num_inst), num_inst <= 32),
+ * m = field / (sum_j field_j + 1e-7)  (fusion.py:1439), and the first instance j >= 1 with
+ * m_j > mask_threshold (fusion.py:1443; instance 0 is background and is never selected).
+ * Survivors are stream-compacted: sel_index[k] = i, sel_inst[k] = j, *sel_count = number found
+ * (device; may exceed `capacity`, entries beyond capacity are dropped — call again with more room).
+ * The order of the survivors is not deterministic; sort by index to get the reference's order.
+ *
+ *   dist_out / valid_out   NULL, or dense (n) outputs (what extract_mesh needs)
+ *   mask_key               NULL = no selection (dense outputs only)
+ *   *sel_count             must be zeroed by the caller (device int64)
+ */
+typedef struct D3FGrid {
+    const float* x;       /* (nx) device */
+    const float* y;       /* (ny) device */
+    const float* z;       /* (nz) device */
+    int32_t nx, ny, nz;
+} D3FGrid;
+
+int d3f_sweep_select(const D3FObs* obs, const D3FGrid* grid, const float* pts, int64_t n,
+                     const D3FKey* mask_key, float dist_threshold, float mask_threshold,
+                     float* dist_out, uint8_t* valid_out,
+                     int64_t capacity, int64_t* sel_count, int32_t* sel_index, int32_t* sel_inst,
+                     uint32_t flags, float mu, void* stream);
+
+/* ---- Multi-GPU: one process per GPU of one box ------------------------------------------------
+ * The reference is single-device (fusion.py:203).  Every query point is independent, so the path
+ * shards over the points with no data-path collective; what callers need on every
+ * GPU is only the compact field: dist (4 B/point) and valid_mask (1 B/point).  A D3FComm holds one
+ * cudaMalloc'ed segment per rank, mapped into every peer with CUDA IPC (NVLink peer access): the
+ * field kernel stores each point's dist / valid straight into the gathered arrays of ALL ranks
+ * (plain remote st.global, 5 B/point/peer against 4 KB/point of local descriptor rows), and the
+ * last CTA of the launch publishes a per-rank epoch flag to every peer (fence.sys + st.release.sys)
+ * and waits for theirs (ld.acquire.sys) — the gather costs no second kernel, no NCCL call and no
+ * extra stream.  Gathered arrays are double-buffered: the result of call k stays valid until
+ * call k+2 is issued.
+ *
+ * Setup is collective and host-synchronised by the caller (torch.distributed in the mirror):
+ *   1. every rank: d3f_comm_create(rank, world, capacity, &comm, handle)      -> 64-byte IPC handle
+ *   2. exchange the handles (all-gather of D3F_IPC_HANDLE_BYTES bytes per rank, rank order)
+ *   3. every rank: d3f_comm_connect(comm, all_handles); then a host barrier.
+ */
+typedef struct D3FComm D3FComm;
+
+int d3f_comm_create(int32_t rank, int32_t world, int64_t capacity_points, int64_t staging_bytes,
+                    D3FComm** comm, void* handle_out);
+int d3f_comm_connect(D3FComm* comm, const void* handles);
+int d3f_comm_destroy(D3FComm* comm);
+/* 0, or D3F_ETIMEOUT if a wait inside a kernel of this communicator gave up (a peer never arrived).
+ * Synchronises `stream` first. */
+int d3f_comm_status(D3FComm* comm, void* stream);
+
+/* d3f_eval over this rank's n points + in-kernel all-gather of dist / valid_mask.  Local point i
+ * lands at gathered index  gather_base + (i / gather_block) * gather_stride + i % gather_block
+ * (contiguous slab: base = slab start, block >= n; blocks dealt round-robin: base = rank*block,
+ * stride = world*block), so the gathered arrays come out in canonical point order with no
+ * re-ordering pass.  *dist_all / *valid_all receive the LOCAL device addresses of the gathered
+ * arrays of this call (capacity_points elements each), complete for all ranks once the launch has
+ * finished on `stream`.  Collective: every rank must call it the same number of times. */
+int d3f_eval_allgather(D3FComm* comm, const D3FObs* obs, const float* pts, int64_t n,
+                       const D3FKey* keys, int32_t n_keys, float* const* out,
+                       int64_t gather_base, int64_t gather_block, int64_t gather_stride,
+                       uint32_t flags, float mu, void* stream,
+                       float** dist_all, uint8_t** valid_all);
+
+/* Replicate `bytes` bytes at `buf` (device) from rank `root` to every rank — the observation after
+ * Fusion.update() on one rank (SURVEY.md 8e "replicate once per update()").  Chunks travel through
+ * the communicator's staging area with copy-engine P2P writes; flags order them.  Collective,
+ * asynchronous on `stream`. */
+int d3f_comm_broadcast(D3FComm* comm, void* buf, int64_t bytes, int32_t root, void* stream);
+
 /* Diagnostics */
 int         d3f_abi_version(void);
 const char* d3f_last_error(void);
@@ -140,6 +256,9 @@ const char* d3f_last_error(void);
 int64_t     d3f_launch_count(void);
 /* name of the kernel variant the last d3f_eval used for keys[k] (static string) */
 const char* d3f_last_variant(int32_t k);
+/* sizeof(D3FKey) / sizeof(D3FObs) as compiled into the library: the binding checks its struct layout */
+int         d3f_sizeof_key(void);
+int         d3f_sizeof_obs(void);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,9 @@ What is restated (every step cites the reference line it follows, paths relative
                                    (align_corners=True, padding 'zeros'; nearest / bilinear)
   field_eval()   fusion.py:305-394 Fusion.eval          (eval_dist=False)
                  fusion.py:396-436 Fusion.eval_dist     (eval_dist=True)
+  init_grid()    fusion.py:79-88   create_init_grid (axes computed by torch.arange, as the reference does)
+  select_candidates()  fusion.py:1420-1445 / 1477-1501  the candidate search of select_features_rand /
+                                   select_features_from_pcd up to (not including) farthest-point sampling
 
 Third-party arithmetic not under /root/reference: torch (reference pins pytorch=2.1.0 in
 env.yaml:11; this image has 2.11.0).  The two torch ops whose rounding decides integer
@@ -205,3 +208,45 @@ def field_eval(pts: np.ndarray, pose: np.ndarray, K: np.ndarray, depth: np.ndarr
         else:
             res[k] = np.concatenate(parts, 0)
     return res
+
+
+def init_grid(boundaries: dict, step: float):
+    """reference fusion.py:79-88 create_init_grid: (coords (N,3) f32, shape, (x,y,z) axis arrays).  The axis values
+    are torch.arange's (float32, vectorised CPU kernel) plus step/2 — computed with torch itself, which is the
+    third-party arithmetic the reference uses here."""
+    import torch
+    axes = [(torch.arange(boundaries[a + '_lower'], boundaries[a + '_upper'], step, dtype=torch.float32) + step / 2).numpy()
+            for a in ('x', 'y', 'z')]
+    xx, yy, zz = np.meshgrid(*axes, indexing='ij')
+    return np.ascontiguousarray(np.stack([xx, yy, zz], -1).reshape(-1, 3)), xx.shape, axes
+
+
+def select_candidates(pts: np.ndarray, pose, K, depth, H: int, W: int, mask: np.ndarray, mu: float = 0.02,
+                      dist_threshold: float = 0.005, mask_threshold: float = 0.6, field_fn=None):
+    """reference fusion.py:1428-1445 (select_features_rand) == :1484-1501 (select_features_from_pcd):
+
+        out = batch_eval(pts, ['mask']);  dist_mask = |out.dist| < 0.005
+        m = out.mask / (out.mask.sum(dim=1, keepdim=True) + 1e-7)
+        for i in 1..num_inst-1:  selected_i = (m[:, i] > 0.6) & dist_mask & out.valid_mask
+
+    Returns (index (K,) int64 ascending, inst (K,) int64, margin (N,) f32 = min_i |m_i - threshold| over i >= 1 for
+    points inside the shell, +inf elsewhere — the distance of each point's decision from the threshold).
+    torch's sum(dim=1) over the instance axis is sequential for num_inst <= 4 and == 8 (measured against torch 2.11
+    CPU); other widths use a vector-width dependent cascade, i.e. the reference's own sum is defined to 1 ulp there.
+    field_fn: alternative implementation of field_eval (e.g. the C oracle) with the same signature."""
+    fe = field_fn or field_eval
+    out = fe(pts, pose, K, depth, H, W, {'mask': mask}, ['mask'], mu=mu)
+    m = out['mask'].astype(F32)
+    shell = (np.abs(out['dist']) < _f(dist_threshold)) & out['valid_mask']
+    s = np.zeros(m.shape[0], dtype=F32)
+    for j in range(m.shape[1]):
+        s = (s + m[:, j]).astype(F32)
+    mn = (m / (s + _f(1e-7)).astype(F32)[:, None]).astype(F32)
+    inst = np.zeros(m.shape[0], dtype=np.int64)
+    for i in range(m.shape[1] - 1, 0, -1):
+        inst[(mn[:, i] > _f(mask_threshold)) & shell] = i
+    margin = np.full(m.shape[0], np.inf, dtype=F32)
+    if m.shape[1] > 1:
+        margin[shell] = np.abs(mn[shell, 1:] - _f(mask_threshold)).min(1)
+    idx = np.nonzero(inst > 0)[0]
+    return idx, inst[idx], margin

@@ -138,10 +138,77 @@ def run_reference(case):
     return o
 
 
+SELECT_CASES = {
+    # name -> scene kwargs, boundaries, grid resolution (None: explicit points), thresholds
+    'select_grid': dict(make=dict(V=4, H=240, W=320, seed=11, feat=None, num_inst=5, color=False),
+                        boundaries=dict(x_lower=-0.4, x_upper=0.4, y_lower=-0.4, y_upper=0.3, z_lower=-0.2, z_upper=0.3),
+                        res=0.005, mu=0.02),
+    'select_pcd': dict(make=dict(V=3, H=120, W=160, seed=12, feat=None, num_inst=8, color=False),
+                       boundaries=None, res=None, mu=0.02),
+}
+
+
+def select_points(name, scene):
+    """Explicit point cloud of the select_features_from_pcd case: jittered samples of the analytic surfaces."""
+    rs = np.random.RandomState(4242)
+    n = 40000
+    th, ph = rs.uniform(0, 2 * np.pi, n), np.arccos(rs.uniform(0.0, 1.0, n))
+    sph = 0.25 * np.stack([np.sin(ph) * np.cos(th), np.sin(ph) * np.sin(th), np.cos(ph)], -1)
+    pl = np.stack([rs.uniform(-0.4, 0.4, n), rs.uniform(-0.4, 0.4, n), np.full(n, -0.1)], -1)
+    pts = np.concatenate([sph, pl], 0) + rs.normal(0, 0.004, (2 * n, 3))
+    return np.ascontiguousarray(pts.astype(np.float32))
+
+
+def run_reference_select(name):
+    """The reference's own lines fusion.py:1420-1445 (1484-1501 for an explicit cloud), executed with its
+    create_init_grid / Fusion.batch_eval, up to the per-instance boolean selection (FPS excluded)."""
+    import torch
+    c = SELECT_CASES[name]
+    mk = c['make']
+    sc = S.make_scene(mk['V'], mk['H'], mk['W'], seed=mk['seed'], feat=None, num_inst=mk['num_inst'])
+    F = RL.reference_fusion(sc, 'cpu')
+    F.mu = c['mu']
+    ref = RL.load_reference()
+    dist_threshold = 0.005
+    if c['res'] is not None:
+        grid, grid_shape = ref.create_init_grid(c['boundaries'], c['res'])
+        grid = grid.to('cpu', dtype=torch.float32)
+    else:
+        grid, grid_shape = torch.from_numpy(select_points(name, sc)), None
+    with torch.no_grad():
+        out = F.batch_eval(grid, return_names=['mask'])
+    dist_mask = torch.abs(out['dist']) < dist_threshold
+    mask = out['mask']
+    mask = mask / (mask.sum(dim=1, keepdim=True) + 1e-7)
+    sel = {}
+    for i in range(1, mk['num_inst']):
+        instance_mask = mask[:, i] > 0.6
+        sel[i] = torch.nonzero(instance_mask & dist_mask & out['valid_mask'])[:, 0].numpy().astype(np.int32)
+    shell = dist_mask & out['valid_mask']
+    margin = (mask[:, 1:] - 0.6).abs().min(dim=1).values
+    near = torch.nonzero(shell & (margin < 2e-5))[:, 0].numpy().astype(np.int32)
+    meta = dict(name=name, make=mk, boundaries=c['boundaries'], res=c['res'], mu=c['mu'], N=int(grid.shape[0]),
+                grid_shape=list(grid_shape) if grid_shape is not None else None, torch=torch.__version__,
+                reference='WangYixuan12/d3fields fusion.py:1420-1445 ops on create_init_grid + Fusion.batch_eval (unmodified, CPU)',
+                input_sha256={'pts': _sha(grid.numpy()), 'depth': _sha(sc.depth), 'mask': _sha(sc.maps['mask'])},
+                shell=int(shell.sum()), dist_sha256=_sha(out['dist'].numpy()), valid_sha256=_sha(out['valid_mask'].numpy()))
+    blob = {'near': near, 'meta': np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)}
+    for i, v in sel.items():
+        blob[f'sel.{i}'] = v
+    path = os.path.join(GOLDEN_DIR, name + '.npz')
+    np.savez_compressed(path, **blob)
+    print(f'{name}: N={grid.shape[0]} shell={int(shell.sum())} selected={[len(v) for v in sel.values()]} near={len(near)} '
+          f'-> {path} ({os.path.getsize(path) / 1024:.0f} KiB)')
+
+
 def main():
     import torch
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if '--select-only' in sys.argv:
+        for name in SELECT_CASES:
+            run_reference_select(name)
+        return
     for name, case in cases().items():
         sc = case['scene']
         ref = run_reference(case)
@@ -172,6 +239,8 @@ def main():
         path = os.path.join(GOLDEN_DIR, name + '.npz')
         np.savez_compressed(path, **blob)
         print(f'{name}: N={N} valid={ref["valid_mask"].mean():.3f} -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)')
+    for name in SELECT_CASES:
+        run_reference_select(name)
 
 
 if __name__ == '__main__':

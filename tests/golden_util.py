@@ -102,3 +102,45 @@ class Golden:
         a64 = a.astype(np.float64)
         assert abs(a64.sum() - s) <= rtol * max(sa, 1e-30) * 1e-2 + 1e-9, (key, a64.sum(), s)
         assert abs(np.abs(a64).sum() - sa) <= rtol * max(sa, 1e-30), (key, np.abs(a64).sum(), sa)
+
+
+SELECT_CASES = ['select_grid', 'select_pcd']
+
+
+class SelectGolden:
+    """tests/golden/select_*.npz: the reference's candidate sets (fusion.py:1420-1445 run on the unmodified
+    reference by oracle/gen_golden.py run_reference_select)."""
+
+    def __init__(self, name):
+        blob = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz')))
+        self.meta = json.loads(bytes(blob['meta']).decode())
+        mk = self.meta['make']
+        self.scene = S.make_scene(mk['V'], mk['H'], mk['W'], seed=mk['seed'], feat=None, num_inst=mk['num_inst'])
+        self.boundaries, self.res, self.mu = self.meta['boundaries'], self.meta['res'], self.meta['mu']
+        self.num_inst = mk['num_inst']
+        self.sel = {i: blob[f'sel.{i}'].astype(np.int64) for i in range(1, self.num_inst)}
+        self.near = set(blob['near'].tolist())
+        assert _sha(self.scene.depth) == self.meta['input_sha256']['depth']
+        assert _sha(self.scene.maps['mask']) == self.meta['input_sha256']['mask']
+
+    def points(self):
+        if self.res is not None:
+            from oracle.field_oracle import init_grid
+            pts, shape, _ = init_grid(self.boundaries, self.res)
+            assert list(shape) == self.meta['grid_shape']
+        else:
+            from oracle.gen_golden import select_points
+            pts = select_points(self.meta['name'], self.scene)
+        assert _sha(pts) == self.meta['input_sha256']['pts'], 'regenerated points differ from the reference run'
+        return pts
+
+    def check(self, index, inst):
+        """(index, inst) of an implementation against the reference's per-instance sets: identical, except points
+        the reference itself decided within 2e-5 of the mask threshold (none in the committed fixtures)."""
+        index, inst = np.asarray(index, dtype=np.int64), np.asarray(inst, dtype=np.int64)
+        assert (np.diff(index) > 0).all(), 'indices must be ascending and unique'
+        for i in range(1, self.num_inst):
+            got, ref = set(index[inst == i].tolist()), set(self.sel[i].tolist())
+            diff = (got ^ ref) - self.near
+            assert not diff, f'instance {i}: {len(diff)} points differ from the reference selection, e.g. {sorted(diff)[:5]}'
+        assert set(np.unique(inst).tolist()) <= set(range(1, self.num_inst))

@@ -4,7 +4,7 @@ GPU box is then compared with the oracle and with the same fixtures."""
 import numpy as np
 import pytest
 
-from golden_util import CASES, EXTRA_CASES, Golden
+from golden_util import CASES, EXTRA_CASES, SELECT_CASES, Golden, SelectGolden
 from oracle import field_oracle as O
 
 
@@ -86,3 +86,21 @@ def test_c_oracle_matches_reference_golden_and_numpy_oracle(name):
             if inter:
                 assert np.array_equal(out[k + '_inter'], ref[k + '_inter']), k
             assert np.abs(out[k] - ref[k]).max() <= 1e-6 * max(1.0, np.abs(ref[k]).max())
+
+
+@pytest.mark.parametrize('name', SELECT_CASES)
+def test_select_candidates_oracle_matches_reference_selection(name):
+    """oracle/field_oracle.select_candidates (restating fusion.py:1428-1445) picks exactly the points the unmodified
+    reference picked; the point coordinates of init_grid are the reference's create_init_grid bytes."""
+    from oracle import c_oracle as CO
+    g = SelectGolden(name)
+    sc = g.scene
+    pts = g.points()
+    idx, inst, margin = O.select_candidates(pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps['mask'], mu=g.mu,
+                                            field_fn=CO.field_eval)
+    g.check(idx, inst)
+    assert len(idx) == sum(len(v) for v in g.sel.values())
+    assert np.isfinite(margin).sum() == g.meta['shell']
+    if name == 'select_pcd':                       # the numpy restatement too, on the small case
+        idx2, inst2, _ = O.select_candidates(pts, sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps['mask'], mu=g.mu)
+        assert np.array_equal(idx, idx2) and np.array_equal(inst, inst2)

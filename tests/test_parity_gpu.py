@@ -277,8 +277,8 @@ def test_sharded_helper_single_rank_writes_in_place():
     f = make_fusion(sc, DEV)
     seen = {}
 
-    def eval_fn(local, names, out):
-        r = f.eval(local, return_names=names, out=out)
+    def eval_fn(local, return_names, return_inter=False, out=None):
+        r = f.eval(local, return_names=return_names, return_inter=return_inter, out=out)
         seen.update({k: (r[k].data_ptr(), out[k].data_ptr()) for k in out})
         return r
 
@@ -288,6 +288,42 @@ def test_sharded_helper_single_rank_writes_in_place():
     assert all(a == b for a, b in seen.values())
     for k in ('dist', 'valid_mask', 'mask', 'dino_feats'):
         assert torch.equal(got[k], ref[k]), k
+    assert not any(k.endswith('_inter') for k in got)
+    # the bound Fusion.eval passed directly (what the docs show): still the tile kernel, still in place
+    got2 = eval_sharded(f.eval, pts, ['dino_feats'], gather=('dist', 'valid_mask'))
+    assert _native.last_variant(0) == 'tile/wide'
+    assert torch.equal(got2['dino_feats'], ref['dino_feats']) and torch.equal(got2['dist'], ref['dist'])
+    assert not any(k.endswith('_inter') for k in got2)
+
+
+def test_peer_comm_single_rank_gather_matches_eval():
+    """d3f_eval_allgather at world size 1 (the in-kernel gather path with its epoch flags, no peers): contiguous
+    and block-interleaved index maps land every point at its canonical position, twice in a row (double buffer)."""
+    from d3fields_b200.sharded import PeerComm, eval_sharded, plan_share
+    sc = S.make_scene(4, 120, 160, seed=33, feat=(12, 16, 128), num_inst=4)
+    pts = torch.from_numpy(np.concatenate([S.grid_points(20, 20, 20), S.scattered_points(777, 5)])).to(DEV)
+    f = make_fusion(sc, DEV)
+    ref = f.eval(pts, return_names=['dino_feats'])
+    comm = PeerComm(len(pts), device=DEV, staging_bytes=1 << 20)
+    try:
+        for rep in range(3):
+            got = eval_sharded(f.eval, pts, ['dino_feats'], comm=comm)
+            comm.check()
+            assert got['shard'] == (0, len(pts))
+            for k in ('dist', 'valid_mask', 'dino_feats'):
+                assert torch.equal(got[k], ref[k]), (rep, k)
+        share = plan_share(pts[:8000], block=400)
+        got = eval_sharded(f.eval, None, [], comm=comm, share=share)
+        comm.check()
+        assert torch.equal(got['dist'], ref['dist'][:8000]) and torch.equal(got['valid_mask'], ref['valid_mask'][:8000])
+        got = eval_sharded(f.eval, pts[:0], [], comm=comm)          # a rank without points still joins the exchange
+        comm.check()
+        assert got['dist'].numel() == 0
+        t = torch.arange(1000, device=DEV, dtype=torch.float32)
+        comm.broadcast(t, root=0)                                    # world 1: a no-op
+        assert t[999].item() == 999
+    finally:
+        comm.close()
 
 
 @pytest.mark.parametrize('C,k', [(1024, 3), (256, 4), (128, 1), (64, 8), (7, 2)])

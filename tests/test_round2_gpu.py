@@ -1,0 +1,252 @@
+"""GPU parity of the round-2 additions, all through Fusion -> ctypes -> C ABI:
+
+  * the fused sweep + threshold + compaction (d3f_sweep_select) against the reference's own candidate sets
+    (tests/golden/select_*.npz, fusion.py:1420-1445) and against eval-then-threshold on the device,
+  * binned traversal (d3f_bin_order / d3f_eval_ordered): a permutation, results bit-identical to the plain launch,
+  * strided maps (D3FKey.stride_*): a crop of a larger tensor sampled in place == its contiguous copy,
+  * the backward against an fp64 reference (how far fp32 autograd itself is from the truth sets the bar),
+  * full-size parity of BASELINE.json's other configs: cfg3 (1M points, mask 480x640x8, f32 and u8) everywhere,
+    cfg2b (5 GB full-resolution volume, the L1-prefetch walk) on sampled rows,
+  * d3f_eval_host from two threads at once.
+"""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from d3fields_b200 import _native, scene as S
+from golden_util import SELECT_CASES, SelectGolden, _sha
+from oracle import c_oracle as CO
+from oracle import field_oracle as O
+from util import assert_bits_equal, assert_close_field, make_fusion
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+# ---------------------------------------------------------------------------- sweep + compaction
+@pytest.mark.parametrize('name', SELECT_CASES)
+@pytest.mark.parametrize('mask_u8', [False, True])
+def test_sweep_select_matches_reference_selection(name, mask_u8):
+    g = SelectGolden(name)
+    f = make_fusion(g.scene, DEV, mask_u8=mask_u8, mu=g.mu)
+    if g.res is not None:
+        got = f.sweep_select(g.boundaries, g.res, dense=True)
+        assert list(got['grid_shape']) == g.meta['grid_shape']
+        pts = g.points()
+    else:
+        pts = g.points()
+        got = f.sweep_select(pts=torch.from_numpy(pts).to(DEV), dense=True)
+    g.check(got['index'].cpu().numpy(), got['inst'].cpu().numpy())
+    assert got['count'] == sum(len(v) for v in g.sel.values())
+    # the dense outputs are the reference's batch_eval bytes (extract_mesh's input, fusion.py:1321)
+    assert _sha(got['dist'].cpu().numpy()) == g.meta['dist_sha256']
+    assert _sha(got['valid_mask'].cpu().numpy()) == g.meta['valid_sha256']
+    # selected coordinates are the grid's own bytes
+    assert np.array_equal(got['pts'].cpu().numpy(), pts[got['index'].cpu().numpy()])
+
+
+def test_sweep_select_equals_eval_then_threshold_and_regrows_capacity():
+    sc = S.make_scene(4, 240, 320, seed=77, num_inst=8)
+    f = make_fusion(sc, DEV, mask_u8=True)
+    b = dict(x_lower=-0.3, x_upper=0.3, y_lower=-0.3, y_upper=0.3, z_lower=-0.15, z_upper=0.28)
+    from d3fields_b200 import create_init_grid
+    grid, shape = create_init_grid(b, 0.004)
+    out = f.eval(grid.to(DEV), return_names=['mask'])
+    m = out['mask'] / (out['mask'].sum(dim=1, keepdim=True) + 1e-7)
+    shell = (out['dist'].abs() < 0.005) & out['valid_mask']
+    want = {i: torch.nonzero((m[:, i] > 0.6) & shell)[:, 0] for i in range(1, 8)}
+    for cap in (None, 1):                               # cap=1 forces the "count > capacity -> call again" path
+        got = f.sweep_select(b, 0.004, capacity=cap)
+        assert tuple(got['grid_shape']) == tuple(shape)
+        margin = (m[:, 1:] - 0.6).abs().min(dim=1).values
+        near = set(torch.nonzero(shell & (margin < 2e-5))[:, 0].tolist())
+        for i in range(1, 8):
+            a = set(got['index'][got['inst'] == i].tolist())
+            assert not ((a ^ set(want[i].tolist())) - near), i
+        assert got['count'] > 1000
+    # selection off: dense outputs only
+    d = f.sweep_select(b, 0.004, mask_name=None, dense=True)
+    assert torch.equal(d['dist'], out['dist']) and torch.equal(d['valid_mask'], out['valid_mask']) and d['count'] == 0
+
+
+# ---------------------------------------------------------------------------- binned traversal
+@pytest.mark.parametrize('n', [1, 5, 300, 70001])
+def test_binned_walk_is_a_permutation_and_bit_identical(n):
+    sc = S.make_scene(4, 240, 320, seed=81, feat=(24, 32, 256), num_inst=4, color=True)
+    f = make_fusion(sc, DEV, mask_u8=True)
+    pts_np = S.scattered_points(n, 81)
+    if n > 100:
+        pts_np[7] = [np.nan, 0, 0]
+        pts_np[11] = [np.inf, -np.inf, 1e30]
+        pts_np[13:40] = pts_np[12]                      # a pile of identical points: one crowded bin
+    pts = torch.from_numpy(pts_np).to(DEV)
+    order = f.bin_order(pts)
+    assert order.dtype == torch.int32 and torch.equal(torch.sort(order.long()).values, torch.arange(n, device=DEV))
+    names = ['dino_feats', 'mask', 'color_tensor']
+    ref = f.eval(pts, return_names=names)
+    for binned in (True, 0.02, order):
+        got = f.eval(pts, return_names=names, binned=binned)
+        for k in ['dist', 'valid_mask'] + names:
+            a, b = got[k].cpu().numpy(), ref[k].cpu().numpy()
+            assert np.array_equal(a, b, equal_nan=True), (k, binned if not isinstance(binned, torch.Tensor) else 'tensor')
+    if n > 1000:                                        # neighbours in the binned sequence are neighbours in space
+        p = pts_np[order.cpu().numpy()]
+        ok = np.isfinite(p).all(1)
+        step = np.linalg.norm(np.diff(p[ok], axis=0), axis=1)
+        raw = np.linalg.norm(np.diff(pts_np[np.isfinite(pts_np).all(1)], axis=0), axis=1)
+        assert np.median(step) < 0.2 * np.median(raw)
+
+
+# ---------------------------------------------------------------------------- strided maps
+def test_strided_maps_sampled_in_place_equal_their_contiguous_copies():
+    sc = S.make_scene(4, 120, 160, seed=91, feat=(12, 16, 128), num_inst=4, color=True)
+    pts_np = np.concatenate([S.grid_points(20, 20, 20), S.scattered_points(3000, 91), S.adversarial_points(sc, 91, 8)])
+    pts = torch.from_numpy(pts_np).to(DEV)
+    f = make_fusion(sc, DEV, mask_u8=True)
+    names = ['dino_feats', 'mask', 'color_tensor']
+    ref = f.eval(pts, return_names=names)
+    ref_i = f.eval(pts, return_names=names, return_inter=True)
+    g = make_fusion(sc, DEV, mask_u8=True)
+    for k in names:                                     # every map becomes a window of a larger, padded tensor
+        t = g.curr_obs_torch[k]
+        V, h, w, C = t.shape
+        pad_c = 4 if C % 4 == 0 else 1
+        big = torch.full((V + 1, h + 3, w + 8, C + pad_c), 99, dtype=t.dtype, device=DEV)
+        big[:V, 1:h + 1, 4:w + 4, :C] = t
+        g.curr_obs_torch[k] = big[:V, 1:h + 1, 4:w + 4, :C]
+        assert not g.curr_obs_torch[k].is_contiguous()
+    got = g.eval(pts, return_names=names)
+    assert [_native.last_variant(i) for i in range(3)] == ['tile/wide', 'tile/narrow', 'tile/narrow']
+    for k in ['dist', 'valid_mask'] + names:
+        assert torch.equal(got[k], ref[k]), k
+    got_i = g.eval(pts, return_names=names, return_inter=True)           # the generic kernel
+    for k in names:
+        assert torch.equal(got_i[k + '_inter'], ref_i[k + '_inter']) and torch.equal(got_i[k], ref_i[k]), k
+    # backward through a strided map
+    G = torch.randn(len(pts), 128, device=DEV, generator=torch.Generator(DEV).manual_seed(1))
+    p1 = pts.clone().requires_grad_(True)
+    (f.eval(p1, return_names=['dino_feats'])['dino_feats'] * G).sum().backward()
+    p2 = pts.clone().requires_grad_(True)
+    (g.eval(p2, return_names=['dino_feats'])['dino_feats'] * G).sum().backward()
+    assert torch.equal(p1.grad, p2.grad)
+    # a map whose channel axis is not dense is refused
+    g.curr_obs_torch['mask'] = g.curr_obs_torch['mask'].permute(0, 1, 3, 2)
+    with pytest.raises(ValueError):
+        g.eval(pts, return_names=['mask'])
+
+
+# ---------------------------------------------------------------------------- backward vs fp64
+def test_backward_error_is_fp32_rounding_measured_against_fp64():
+    """The 2e-3 bar of round 1 compared two float32 computations with each other.  Here the truth is the reference
+    operator sequence differentiated in float64; d3f_eval_backward must be as close to it as torch's own float32
+    autograd is (both sum ~1000 signed products per point; neither is exact)."""
+    from oracle import torch_port as TP
+    sc = S.make_scene(4, 240, 320, seed=52, feat=(24, 32, 1024))
+    rs = np.random.RandomState(52)
+    base = S.grid_points(60, 60, 40)
+    ref0 = O.field_eval(base, sc.pose, sc.K, sc.depth, sc.H, sc.W)
+    near = base[np.abs(ref0['dist']) < 0.0199][::11][:800]
+    pts_np = np.concatenate([near, near + rs.normal(0, 0.03, near.shape).astype(np.float32)])
+    n = len(pts_np)
+    Gf = rs.standard_normal((n, 1024)).astype(np.float32)
+    gd = rs.standard_normal(n).astype(np.float32)
+
+    def torch_grad(dtype):
+        obs = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in TP.obs_from_scene(sc).items()}
+        p = torch.from_numpy(pts_np).to(dtype).requires_grad_(True)
+        o = TP.eval_chunk(obs, sc.H, sc.W, p, ['dino_feats'])
+        ((o['dino_feats'] * torch.from_numpy(Gf).to(dtype)).sum() + (o['dist'] * torch.from_numpy(gd).to(dtype)).sum()).backward()
+        return p.grad.numpy().astype(np.float64), o['dist'].detach().numpy().astype(np.float64)
+
+    g64, d64 = torch_grad(torch.float64)
+    g32, d32 = torch_grad(torch.float32)
+    f = make_fusion(sc, DEV)
+    p = torch.from_numpy(pts_np).to(DEV).requires_grad_(True)
+    out = f.eval(p, return_names=['dino_feats'])
+    ((out['dino_feats'] * torch.from_numpy(Gf).to(DEV)).sum() + (out['dist'] * torch.from_numpy(gd).to(DEV)).sum()).backward()
+    g = p.grad.cpu().numpy().astype(np.float64)
+    # points whose hard decisions (nearest pixel, visibility, clamp side) differ between fp64 and fp32 are different
+    # functions, not rounding: leave them out
+    same = np.abs(d64 - d32) < 1e-6
+    assert same.mean() > 0.97
+    scale = np.abs(g64[same]).max()
+    e_ours = np.abs(g - g64)[same].max() / scale
+    e_t32 = np.abs(g32 - g64)[same].max() / scale
+    print(f'backward vs fp64: ours {e_ours:.2e}, torch fp32 autograd {e_t32:.2e} (relative to max |grad| {scale:.3g})')
+    assert e_ours <= max(3 * e_t32, 2e-6), (e_ours, e_t32)
+    rel_rms = np.sqrt(((g - g64)[same] ** 2).mean()) / np.sqrt((g64[same] ** 2).mean())
+    assert rel_rms < 1e-5, rel_rms
+
+
+# ---------------------------------------------------------------------------- full-size parity of cfg3 / cfg2b
+@pytest.mark.parametrize('mask_u8', [False, True])
+def test_full_size_cfg3_mask_field_matches_oracle_everywhere(mask_u8):
+    c = S.CONFIGS['cfg3']
+    sc = S.make_scene(c['V'], c['H'], c['W'], seed=0, num_inst=c['num_inst'])
+    pts_np = S.config_points('cfg3')
+    f = make_fusion(sc, DEV, mask_u8=mask_u8)
+    out = f.eval(torch.from_numpy(pts_np).to(DEV), return_names=['mask'])
+    assert _native.last_variant(0) == 'tile/narrow'
+    ref = CO.field_eval(pts_np, sc.pose, sc.K, sc.depth, sc.H, sc.W, sc.maps, ['mask'])
+    assert_bits_equal(out['dist'].cpu().numpy(), ref['dist'], 'dist')
+    assert_bits_equal(out['valid_mask'].cpu().numpy(), ref['valid_mask'], 'valid_mask')
+    assert_close_field(out['mask'].cpu().numpy(), ref['mask'], what='mask (1M x 8)')
+    assert 0.2 < ref['valid_mask'].mean() < 0.9
+
+
+def test_full_size_cfg2b_full_resolution_volume_prefetch_walk():
+    """cfg2b: the descriptor volume at image resolution (4 x 480 x 640 x 1024 f32 = 5 GB, not L2-resident), which
+    selects the L1-prefetch instantiation of the wide walk (field_tile_kernel<.,4,true,.>).  1M grid points on the
+    device; dist / valid everywhere and 2000 sampled descriptor rows against the C oracle."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 14 << 30:
+        pytest.skip('needs 14 GB of free device memory')
+    V, H, W, C = 4, 480, 640, 1024
+    sc = S.make_scene(V, H, W, seed=0)
+    gen = torch.Generator(DEV).manual_seed(1234)
+    vol = torch.randn((V, H, W, C), dtype=torch.float32, device=DEV, generator=gen)
+    f = make_fusion(sc, DEV)
+    f.curr_obs_torch['dino_feats'] = vol
+    pts_np = S.config_points('cfg2a')
+    out = f.eval(torch.from_numpy(pts_np).to(DEV), return_names=['dino_feats'])
+    assert _native.last_variant(0) == 'tile/wide'
+    ref = CO.field_eval(pts_np, sc.pose, sc.K, sc.depth, H, W)
+    assert_bits_equal(out['dist'].cpu().numpy(), ref['dist'], 'dist')
+    assert_bits_equal(out['valid_mask'].cpu().numpy(), ref['valid_mask'], 'valid_mask')
+    rows = np.unique(np.concatenate([np.linspace(0, len(pts_np) - 1, 1500).astype(np.int64),
+                                     np.nonzero(ref['valid_mask'])[0][::400][:1500]]))
+    vol_h = vol.cpu().numpy()
+    ref_rows = CO.field_eval(pts_np[rows], sc.pose, sc.K, sc.depth, H, W, {'dino_feats': vol_h}, ['dino_feats'])
+    assert_close_field(out['dino_feats'][torch.from_numpy(rows).to(DEV)].cpu().numpy(), ref_rows['dino_feats'], what='cfg2b rows')
+    # scattered + binned on the same volume
+    sp = torch.from_numpy(S.scattered_points(50000, 3)).to(DEV)
+    a, b = f.eval(sp, return_names=['dino_feats']), f.eval(sp, return_names=['dino_feats'], binned=True)
+    assert torch.equal(a['dino_feats'], b['dino_feats']) and torch.equal(a['dist'], b['dist'])
+
+
+# ---------------------------------------------------------------------------- host entry point, two threads
+def test_eval_host_from_two_threads_at_once():
+    sc = S.make_scene(4, 120, 160, seed=95, feat=(12, 16, 128), num_inst=4)
+    f = make_fusion(sc, DEV, mask_u8=True)
+    pts = [torch.from_numpy(S.scattered_points(200000, s)).pin_memory() for s in (1, 2)]
+    want = [f.eval(p.to(DEV), return_names=['dino_feats', 'mask']) for p in pts]
+    got, errs = [None, None], []
+
+    def run(i):
+        try:
+            for _ in range(3):
+                got[i] = f.eval_host(pts[i], ['dino_feats', 'mask'])
+        except Exception as e:                          # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i in range(2):
+        for k in ('dist', 'valid_mask', 'dino_feats', 'mask'):
+            assert torch.equal(got[i][k], want[i][k].cpu()), (i, k)
+    _native.release_scratch()
+    assert torch.equal(f.eval_host(pts[0], ['mask'])['mask'], want[0]['mask'].cpu())

@@ -1,6 +1,7 @@
 """CPU, world_size 2 and 3 over gloo: the N>1 host logic — slab partition, in-place gather layout, ragged
 slabs, replication of the observation.  The per-slab evaluation is the CPU oracle here (tests may call it);
-on the GPU box tests/test_parity_gpu.py::test_sharded_* runs the same helper over the CUDA kernels."""
+on the GPU box tests/test_parity_gpu.py::test_sharded_* runs the same helper over the CUDA kernels at world size 1
+and tests/test_multigpu.py spawns real NCCL ranks (2 GPUs) for both transports."""
 import os
 import socket
 
@@ -48,8 +49,10 @@ def _worker(rank, world, port, n, q, block=None):
         pts = torch.from_numpy(S.scattered_points(n, 9))
         maps = {'mask': obs['mask'].numpy(), 'dino_feats': obs['dino_feats'].numpy()}
 
-        def eval_fn(local, names, out):
-            r = O.field_eval(local.numpy(), obs['pose'].numpy(), obs['K'].numpy(), obs['depth'].numpy(), 60, 80, maps, names)
+        def eval_fn(local, return_names, return_inter=False, out=None):          # Fusion.eval's signature
+            assert return_inter is False and isinstance(out, dict)
+            r = O.field_eval(local.numpy(), obs['pose'].numpy(), obs['K'].numpy(), obs['depth'].numpy(), 60, 80, maps,
+                             return_names)
             res = {k: torch.from_numpy(v) for k, v in r.items()}
             if rank == 0:                  # one rank honours `out` (in-place slot), the other returns fresh tensors
                 for k in out:
