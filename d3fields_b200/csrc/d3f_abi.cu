@@ -103,10 +103,28 @@ int validate(const D3FObs* obs, const void* pts, int64_t n, const D3FKey* keys, 
 // Device-pointer evaluation shared by d3f_eval and the slabs of d3f_eval_host.
 __global__ void gather_only_kernel(const d3f::EvalParams ep) { d3f::gather_epilogue(ep); }
 
+template <bool RECIP, int VARIANT, bool WIDE, bool ORDERED>
+cudaError_t launch_tile_inst(dim3 grid, dim3 block, cudaStream_t st, const d3f::EvalParams& ep, const d3f::KeySet& ks) {
+    constexpr size_t smem = d3f::WALK_FFMA2 ? sizeof(d3f::TileSmemT<WIDE>) : 0;      // static shared memory otherwise
+    // once per instantiation and device: the wide tile needs more than the default 48 KB of dynamic shared memory
+    static std::atomic<uint64_t> opted{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024 && !(opted.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+        e = cudaFuncSetAttribute(d3f::field_tile_kernel<RECIP, VARIANT, WIDE, ORDERED>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        opted.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+    d3f::field_tile_kernel<RECIP, VARIANT, WIDE, ORDERED><<<grid, block, smem, st>>>(ep, ks);
+    return cudaSuccess;
+}
+
 template <bool RECIP, int VARIANT, bool WIDE>
-void launch_tile(bool ordered, dim3 grid, dim3 block, cudaStream_t st, const d3f::EvalParams& ep, const d3f::KeySet& ks) {
-    if (ordered) d3f::field_tile_kernel<RECIP, VARIANT, WIDE, true><<<grid, block, 0, st>>>(ep, ks);
-    else         d3f::field_tile_kernel<RECIP, VARIANT, WIDE, false><<<grid, block, 0, st>>>(ep, ks);
+cudaError_t launch_tile(bool ordered, dim3 grid, dim3 block, cudaStream_t st, const d3f::EvalParams& ep, const d3f::KeySet& ks) {
+    return ordered ? launch_tile_inst<RECIP, VARIANT, WIDE, true>(grid, block, st, ep, ks)
+                   : launch_tile_inst<RECIP, VARIANT, WIDE, false>(grid, block, st, ep, ks);
 }
 
 int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys, int32_t n_keys,
@@ -172,16 +190,18 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
             if (is_wide(k)) wide_bytes += (size_t)obs->V * keys[k].h * keys[k].w * keys[k].C * 4;
         const bool prefetch = force >= 0 ? force != 0 : wide_bytes > (size_t)(64u << 20);
         const bool ord = order != nullptr;
+        cudaError_t le;
         if (wide_bytes == 0) {            // no register-cached walk needed: the light instantiation (4 CTAs/SM)
-            if (recip) launch_tile<true, 0, false>(ord, grid, block, st, ep, ks);
-            else       launch_tile<false, 0, false>(ord, grid, block, st, ep, ks);
+            le = recip ? launch_tile<true, 0, false>(ord, grid, block, st, ep, ks)
+                       : launch_tile<false, 0, false>(ord, grid, block, st, ep, ks);
         } else if (recip) {
-            if (prefetch) launch_tile<true, 4, true>(ord, grid, block, st, ep, ks);
-            else          launch_tile<true, 0, true>(ord, grid, block, st, ep, ks);
+            le = prefetch ? launch_tile<true, 4, true>(ord, grid, block, st, ep, ks)
+                          : launch_tile<true, 0, true>(ord, grid, block, st, ep, ks);
         } else {
-            if (prefetch) launch_tile<false, 4, true>(ord, grid, block, st, ep, ks);
-            else          launch_tile<false, 0, true>(ord, grid, block, st, ep, ks);
+            le = prefetch ? launch_tile<false, 4, true>(ord, grid, block, st, ep, ks)
+                          : launch_tile<false, 0, true>(ord, grid, block, st, ep, ks);
         }
+        if (le != cudaSuccess) return fail(D3F_ECUDA, "tile kernel launch setup failed: %s", cudaGetErrorString(le));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         D3F_CUDA(cudaGetLastError());
         return D3F_OK;

@@ -34,14 +34,27 @@ constexpr int TILE_THREADS = 256;
 constexpr int TILE_PTS = 256;            // measured: 256-point tiles beat 128 by 4 % (half the barriers and cold starts per point)
 constexpr int TILE_V = 4;             // views supported by this kernel (slots are padded to 4)
 
-struct TileSmem {
+// D3F_WALK_FFMA2=1 builds the wide walk with packed FFMA2 accumulation (two channels per instruction, weights stored
+// twice in shared memory, 60 KB dynamic shared memory).  Measured on B200 (profiles/r02_experiment_ffma2.jsonl):
+// bit-identical results, 1.5 % SLOWER on cfg2a and 4 % slower on a fully visible grid — the FP32 pipe is not what
+// limits the walk, and the second LDS.128 per view costs more than the 8 saved issue slots.  Kept for A/B only.
+#ifndef D3F_WALK_FFMA2
+#define D3F_WALK_FFMA2 0
+#endif
+constexpr bool WALK_FFMA2 = D3F_WALK_FFMA2 != 0;
+
+template <bool WIDE>
+struct TileSmemT {
     float H[TILE_V * 12];
     float px[TILE_PTS * TILE_V];
     float py[TILE_PTS * TILE_V];
     float d[TILE_PTS * TILE_V];
     float fac[TILE_PTS * TILE_V];
     int vis[TILE_PTS * TILE_V];
-    float4 w4[TILE_PTS * TILE_V];     // folded corner weights per (point, view)
+    float4 w4[TILE_PTS * TILE_V * ((WIDE && WALK_FFMA2) ? 2 : 1)];
+                                      // folded corner weights per (point, view).  Narrow keys: slot s holds (w_nw, w_ne, w_sw, w_se).
+                                      // Wide keys under D3F_WALK_FFMA2: slots 2s, 2s+1 hold every weight twice,
+                                      // (nw,nw,ne,ne) (sw,sw,se,se) — the operand layout of the packed FFMA2
     int4 code[TILE_PTS + 4];          // packed footprint codes of the 4 views of a point: element offset of the
                                       // north-west texel inside the view (wide maps: a multiple of 4, used as is;
                                       // narrow maps: shifted left by 2) | east-step bit | south-step bit << 1; -1 = unseen
@@ -74,10 +87,27 @@ __host__ __device__ inline int wide_run_len(int S) { const int R = wide_runs(S);
         cc[v][0] = ldg4(b_); cc[v][1] = ldg4(b_ + dx_);                                            \
         cc[v][2] = ldg4(b_ + dy_); cc[v][3] = ldg4(b_ + (dy_ + dx_));                              \
     }
-#define D3F_WIDE_FMA(v, w_)                                                                        \
+// acc (4 channels) += w_corner * texel_corner for the four corners of view v, two channels per FFMA2.
+// sm_100 issues a 3-register FFMA every other cycle per scheduler; the packed form carries two FMAs per issue, which
+// is what lets a fully visible tile run at the HBM rate instead of the FP32 pipe's (measured: DESIGN.md §4.8).
+// Per channel the order of the additions is the same as the scalar form's: nw, ne, sw, se — results are bit-identical.
+#define D3F_WIDE_FMA1(v, w_)                                                                       \
     {                                                                                              \
         fma4(acc, w_.x, cc[v][0]); fma4(acc, w_.y, cc[v][1]);                                      \
         fma4(acc, w_.z, cc[v][2]); fma4(acc, w_.w, cc[v][3]);                                      \
+    }
+#define D3F_WIDE_FMA(v, wa_, wb_)                                                                  \
+    {                                                                                              \
+        const float2 w0_ = make_float2(wa_.x, wa_.y), w1_ = make_float2(wa_.z, wa_.w);             \
+        const float2 w2_ = make_float2(wb_.x, wb_.y), w3_ = make_float2(wb_.z, wb_.w);             \
+        acc01 = __ffma2_rn(make_float2(cc[v][0].x, cc[v][0].y), w0_, acc01);                       \
+        acc23 = __ffma2_rn(make_float2(cc[v][0].z, cc[v][0].w), w0_, acc23);                       \
+        acc01 = __ffma2_rn(make_float2(cc[v][1].x, cc[v][1].y), w1_, acc01);                       \
+        acc23 = __ffma2_rn(make_float2(cc[v][1].z, cc[v][1].w), w1_, acc23);                       \
+        acc01 = __ffma2_rn(make_float2(cc[v][2].x, cc[v][2].y), w2_, acc01);                       \
+        acc23 = __ffma2_rn(make_float2(cc[v][2].z, cc[v][2].w), w2_, acc23);                       \
+        acc01 = __ffma2_rn(make_float2(cc[v][3].x, cc[v][3].y), w3_, acc01);                       \
+        acc23 = __ffma2_rn(make_float2(cc[v][3].z, cc[v][3].w), w3_, acc23);                       \
     }
 
 constexpr int WIDE_LOOKAHEAD = 4;      // points between the L1 prefetch of a cell change and its reload
@@ -86,7 +116,7 @@ constexpr int WIDE_LOOKAHEAD = 4;      // points between the L1 prefetch of a ce
 // then prefetches its own 512-byte slice of those corner texels into L1, so the reload that follows is an L1 hit
 // instead of an L2 round trip with all eight warps of the CTA stalled on the same point.
 template <bool PREFETCH, bool ORDERED>
-__device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmem& sm) {
+__device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<true>& sm) {
     const int C = kp.C;
     const int S = C >> 7;                                   // 128-channel slices
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,6 +168,9 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
                 }
             }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#if D3F_WALK_FFMA2
+            float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
+#endif
             if (m & 0xFFu) {
                 if (m & 0xF0u) {
                     const int4 code = sm.code[p];
@@ -146,16 +179,32 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
                     if (m & 0x40u) D3F_WIDE_RELOAD(2, code.z)
                     if (m & 0x80u) D3F_WIDE_RELOAD(3, code.w)
                 }
+#if D3F_WALK_FFMA2
+                // software-pipelined: the weight reads of view v+2 are issued behind the FMAs of view v, so two views'
+                // weights (16 registers) are in flight at a time
+                float4 wa0, wb0, wa1, wb1;
+                const float4* wp = sm.w4 + (size_t)p * (TILE_V * 2);
+                if (m & 1u) { wa0 = wp[0]; wb0 = wp[1]; }
+                if (m & 2u) { wa1 = wp[2]; wb1 = wp[3]; }
+                if (m & 1u) D3F_WIDE_FMA(0, wa0, wb0)
+                if (m & 4u) { wa0 = wp[4]; wb0 = wp[5]; }
+                if (m & 2u) D3F_WIDE_FMA(1, wa1, wb1)
+                if (m & 8u) { wa1 = wp[6]; wb1 = wp[7]; }
+                if (m & 4u) D3F_WIDE_FMA(2, wa0, wb0)
+                if (m & 8u) D3F_WIDE_FMA(3, wa1, wb1)
+                acc = make_float4(acc01.x, acc01.y, acc23.x, acc23.y);
+#else
                 // the weight reads of every visible view are issued before the first FMA
                 float4 w0, w1, w2, w3;
                 if (m & 1u) w0 = sm.w4[p * TILE_V + 0];
                 if (m & 2u) w1 = sm.w4[p * TILE_V + 1];
                 if (m & 4u) w2 = sm.w4[p * TILE_V + 2];
                 if (m & 8u) w3 = sm.w4[p * TILE_V + 3];
-                if (m & 1u) D3F_WIDE_FMA(0, w0)
-                if (m & 2u) D3F_WIDE_FMA(1, w1)
-                if (m & 4u) D3F_WIDE_FMA(2, w2)
-                if (m & 8u) D3F_WIDE_FMA(3, w3)
+                if (m & 1u) D3F_WIDE_FMA1(0, w0)
+                if (m & 2u) D3F_WIDE_FMA1(1, w1)
+                if (m & 4u) D3F_WIDE_FMA1(2, w2)
+                if (m & 8u) D3F_WIDE_FMA1(3, w3)
+#endif
             }
             if (ORDERED) __stcs(reinterpret_cast<float4*>(o_col + (size_t)sm.row[p] * C), acc);
             else         __stcs(reinterpret_cast<float4*>(o), acc);
@@ -163,8 +212,8 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
     }
 }
 
-template <typename T, int VEC, bool ORDERED>
-__device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmem& sm) {
+template <typename T, int VEC, bool ORDERED, bool WIDE>
+__device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<WIDE>& sm) {
     const int C = kp.C;
     const int G = C / VEC;
     const T* __restrict__ vol = static_cast<const T*>(kp.data);
@@ -221,9 +270,17 @@ __host__ __device__ inline bool key_fits_tile(int dtype, int C, int h, int w, lo
 template <bool RECIP, int VARIANT, bool WIDE, bool ORDERED>
 __global__ void __launch_bounds__(TILE_THREADS, WIDE ? 2 : 4)
 field_tile_kernel(const EvalParams ep, const KeySet ks) {
-    __shared__ TileSmem sm;
+#if D3F_WALK_FFMA2
+    extern __shared__ __align__(16) unsigned char tile_smem_raw[];       // sizeof(TileSmemT<WIDE>), above 48 KB when WIDE
+    TileSmemT<WIDE>& sm = *reinterpret_cast<TileSmemT<WIDE>*>(tile_smem_raw);
+#else
+    __shared__ TileSmemT<WIDE> sm;
+#endif
     const int V = ep.V;
     const bool eval_dist = (ep.flags & D3F_FLAG_EVAL_DIST) != 0;
+    // Tiles are taken in order.  Dealing them to the CTAs with a stride (so that the CTAs resident at one time mix
+    // all-zero store-bound rows with issue-bound visible rows) was measured and is slower: 0.798 vs 0.781 ms on cfg2a,
+    // 2.15 vs 1.92 ms on cfg2b (profiles/r02_experiment_tile_stride.jsonl) — neighbouring tiles share texels in L1/L2.
     const int64_t tile0 = (int64_t)blockIdx.x * TILE_PTS;
     const int npts = (int)min((int64_t)TILE_PTS, ep.n - tile0);
 
@@ -291,7 +348,13 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
             if (p < npts && v < V && sm.vis[s]) {
                 const Footprint f = footprint<RECIP>(sm.px[s], sm.py[s], ep.H, ep.W, kp.h, kp.w);
                 const float fac = sm.fac[s];
-                sm.w4[s] = make_float4(f.w[0] * fac, f.w[1] * fac, f.w[2] * fac, f.w[3] * fac);
+                const float w0 = f.w[0] * fac, w1 = f.w[1] * fac, w2 = f.w[2] * fac, w3 = f.w[3] * fac;
+                if (WIDE && WALK_FFMA2 && wide) {
+                    sm.w4[2 * s] = make_float4(w0, w0, w1, w1);
+                    sm.w4[2 * s + 1] = make_float4(w2, w2, w3, w3);
+                } else {
+                    sm.w4[s] = make_float4(w0, w1, w2, w3);
+                }
                 const int eo = f.y0 * kp.sy + f.x0 * kp.sx;
                 code = (wide ? eo : (eo << 2)) | (f.dx ? 1 : 0) | (f.dy ? 2 : 0);
             }
@@ -330,15 +393,15 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
                 if (threadIdx.x < TILE_PTS) sm.mask[threadIdx.x] |= ahead;
             }
             __syncthreads();
-            wide_accumulate<(VARIANT & 4) != 0, ORDERED>(kp, tile0, npts, sm);
+            if constexpr (WIDE) wide_accumulate<(VARIANT & 4) != 0, ORDERED>(kp, tile0, npts, sm);
         } else {
             const bool vec4 = (kp.C % 4 == 0) && ((kp.sv | kp.sy | kp.sx) & 3) == 0;
             if (ks.dtype[k] == D3F_F32) {
-                if (vec4) narrow_accumulate<float, 4, ORDERED>(kp, tile0, npts, sm);
-                else      narrow_accumulate<float, 1, ORDERED>(kp, tile0, npts, sm);
+                if (vec4) narrow_accumulate<float, 4, ORDERED, WIDE>(kp, tile0, npts, sm);
+                else      narrow_accumulate<float, 1, ORDERED, WIDE>(kp, tile0, npts, sm);
             } else {
-                if (vec4) narrow_accumulate<uint8_t, 4, ORDERED>(kp, tile0, npts, sm);
-                else      narrow_accumulate<uint8_t, 1, ORDERED>(kp, tile0, npts, sm);
+                if (vec4) narrow_accumulate<uint8_t, 4, ORDERED, WIDE>(kp, tile0, npts, sm);
+                else      narrow_accumulate<uint8_t, 1, ORDERED, WIDE>(kp, tile0, npts, sm);
             }
         }
         __syncthreads();

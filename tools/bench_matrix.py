@@ -81,6 +81,76 @@ def main():
     if want('cfg2a_scattered'):
         ms, mn = timed(lambda: f.eval(scat1m, ['dino_feats']), flush=flush)
         rec('cfg2a_scattered', 1_000_000, ms, mn, [(48, 64, 1024, 4)], 'N(0,0.25^2) keypoints, no locality')
+    if want('binned'):
+        # keypoints without spatial order, walked in lattice-cell order (d3f_bin_order + d3f_eval_ordered)
+        ms, mn = timed(lambda: f.eval(scat1m, ['dino_feats'], binned=True), flush=flush)
+        rec('cfg2a_scattered_binned', 1_000_000, ms, mn, [(48, 64, 1024, 4)], 'bin_order (6 launches) + ordered walk, both timed')
+        for cell in (0.005, 0.01, 0.02):
+            ms, mn = timed(lambda: f.eval(scat1m, ['dino_feats'], binned=cell), flush=flush)
+            rec(f'cfg2a_scattered_binned_cell{cell}', 1_000_000, ms, mn, [(48, 64, 1024, 4)])
+        order = f.bin_order(scat1m)
+        ms, mn = timed(lambda: f.eval(scat1m, ['dino_feats'], binned=order), flush=flush)
+        rec('cfg2a_scattered_preordered', 1_000_000, ms, mn, [(48, 64, 1024, 4)], 'order computed once outside the timed call')
+        ms, mn = timed(lambda: f.bin_order(scat1m), flush=flush)
+        rec('bin_order_1m', 1_000_000, ms, mn, [], 'd3f_bin_order alone')
+        ms, mn = timed(lambda: f.eval(scat256k, ['dino_feats'], binned=True), flush=flush)
+        rec('cfg5_frame_256k_scattered_binned', 262144, ms, mn, [(48, 64, 1024, 4)])
+        ms, mn = timed(lambda: f.eval(grid1m, ['dino_feats'], binned=True), flush=flush)
+        rec('cfg2a_grid_binned', 1_000_000, ms, mn, [(48, 64, 1024, 4)], 'a grid gains nothing from binning (already ordered)')
+    if want('visible'):
+        # a scene where most points are seen by some view: points in a shell around the surfaces, z-fastest order kept
+        d = f.eval(grid16m, [])
+        keep = torch.nonzero(d['valid_mask'])[:, 0][:1_000_000]
+        vis1m = grid16m[keep].contiguous()
+        frac = float(f.eval(vis1m, [])['valid_mask'].float().mean())
+        ms, mn = timed(lambda: f.eval(vis1m, ['dino_feats']), flush=flush)
+        rec('cfg2a_grid_all_visible', 1_000_000, ms, mn, [(48, 64, 1024, 4)], f'first 1M grid points (of 16M, z fastest) that some view sees: valid fraction {frac:.3f}')
+        none1m = grid16m[torch.nonzero(~d['valid_mask'])[:, 0][:1_000_000]].contiguous()
+        ms, mn = timed(lambda: f.eval(none1m, ['dino_feats']), flush=flush)
+        rec('cfg2a_grid_none_visible', 1_000_000, ms, mn, [(48, 64, 1024, 4)], 'points no view sees: pure zero-row stream')
+    if want('backward'):
+        kp = torch.from_numpy(S.scattered_points(800, 5, sigma=0.15)).to(DEV)
+        G = torch.randn(800, 1024, device=DEV)
+        def fb():
+            p = kp.clone().requires_grad_(True)
+            o = f.eval(p, ['dino_feats'])
+            ((o['dino_feats'] * G).sum() + o['dist'].sum()).backward()
+        ms, mn = timed(fb, warm=5, reps=20)
+        r = dict(name='tracking_fwd_bwd_800pts_eager', n=800, ms=ms, ms_min=mn, note='autograd Function forward + d3f_eval_backward + torch loss, eager launches')
+        results.append(r); print(json.dumps(r), flush=True)
+        big = scat256k.clone()
+        Gb = torch.randn(262144, 1024, device=DEV)
+        def fb2():
+            p = big.clone().requires_grad_(True)
+            o = f.eval(p, ['dino_feats'])
+            (o['dino_feats'] * Gb).sum().backward()
+        ms, mn = timed(fb2, warm=2, reps=5)
+        r = dict(name='fwd_bwd_256k', n=262144, ms=ms, ms_min=mn, note='forward + backward kernels + torch mul/sum on 256k keypoints')
+        results.append(r); print(json.dumps(r), flush=True)
+    if want('sweep_select'):
+        f.curr_obs_torch['mask'] = f.curr_obs_torch['mask_u8']
+        b = dict(x_lower=-0.4, x_upper=0.4, y_lower=-0.4, y_upper=0.3, z_lower=-0.2, z_upper=-0.019)
+        f.sweep_select(b, 0.001)
+        torch.cuda.synchronize()
+        # kernel only: zero the counter + launch, no host read-back
+        ts = []
+        for _ in range(5):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            r_ = f.sweep_select(b, 0.001)
+            torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+        nbig = int(r_['grid_shape'][0] * r_['grid_shape'][1] * r_['grid_shape'][2])
+        r = dict(name='sweep_select_101m_u8', n=nbig, ms=float(np.median(ts)), ms_min=float(min(ts)), mpts_s=nbig / float(np.median(ts)) / 1e3,
+                 survivors=int(r_['count']), note='d3f_sweep_select end to end (wall clock incl. count read-back, sort of survivors): no grid, no dense mask field in HBM')
+        results.append(r); print(json.dumps(r), flush=True)
+        ts = []
+        for _ in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            r_ = f.sweep_select(b, 0.001, mask_name=None, dense=True)
+            torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+        r = dict(name='sweep_dense_dist_101m', n=nbig, ms=float(np.median(ts)), ms_min=float(min(ts)), mpts_s=nbig / float(np.median(ts)) / 1e3,
+                 note='dense dist/valid from the linear index (extract_mesh input), no pts in HBM')
+        results.append(r); print(json.dumps(r), flush=True)
+        f.curr_obs_torch['mask'] = torch.from_numpy(sc.maps['mask']).to(DEV)
     if want('cfg5_frame'):
         ms, mn = timed(lambda: f.eval(scat256k, ['dino_feats']), flush=flush)
         rec('cfg5_frame_256k_scattered', 262144, ms, mn, [(48, 64, 1024, 4)])
