@@ -35,6 +35,28 @@ import torch.distributed as dist
 from . import _native
 
 
+def bind_to_gpu_numa(device_index: int) -> str:
+    """Pin the calling thread (and the threads it starts later) to the CPU cores next to GPU `device_index`, so the
+    pinned host buffers it allocates afterwards are first-touched on that GPU's NUMA node.  With one rank per GPU and
+    4 GB of results per step crossing PCIe, ranks that share one node's memory controller and root complex do not
+    scale (round 1: 13 -> 57 Mpts/s from 1 to 8 GPUs).  Returns a description of what was done."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return 'gpu-local cpu set is empty under this cgroup: affinity unchanged'
+        os.sched_setaffinity(0, cpus)
+        return f'bound to {len(cpus)} cpus local to gpu {device_index} ({min(cpus)}-{max(cpus)})'
+    except Exception as e:                                  # noqa: BLE001 - best effort
+        return f'affinity unchanged ({type(e).__name__}: {e})'
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous slab of rank `rank`: sizes differ by at most one point, slabs tile [0, n)."""
     return (n * rank) // world, (n * (rank + 1)) // world
