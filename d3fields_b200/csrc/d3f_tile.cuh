@@ -73,6 +73,31 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
     return r;
 }
 
+// Shared-memory reads of the walk go through explicit 32-bit shared addresses that are computed ONCE per walk and
+// pinned in a register (the opaque mov): left to itself the compiler re-derives the CTA's shared-window base
+// (S2UR SR_CgaCtaId + ULEA) in front of every point's weight reads, which puts a special-register read at the head of
+// each point's dependency chain.
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p), r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+    float4 r;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ int4 lds_i4(unsigned a) {
+    int4 r;
+    asm("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ int lds_i(unsigned a) {
+    int r;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+
 // Number of point runs a tile is split into for a map of S 128-channel slices (8 warps per CTA).
 __host__ __device__ inline int wide_runs(int S) { return S >= TILE_THREADS / 32 ? 1 : (TILE_THREADS / 32) / S; }
 __host__ __device__ inline int wide_run_len(int S) { const int R = wide_runs(S); return (TILE_PTS + R - 1) / R; }
@@ -133,6 +158,7 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
     }
     if (p_end <= p_begin) return;
     const float* __restrict__ vol = static_cast<const float*>(kp.data);
+    const unsigned a_mask = smem_addr(sm.mask), a_code = smem_addr(sm.code), a_w4 = smem_addr(sm.w4);
     for (int s = s0; s < S; s += sstep) {
         const float* vbase[TILE_V];
 #pragma unroll
@@ -144,14 +170,14 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
         for (int v = 0; v < TILE_V; ++v)
 #pragma unroll
             for (int q = 0; q < 4; ++q) cc[v][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int m_next = sm.mask[p_begin];
+        int m_next = lds_i(a_mask + p_begin * 4);
         for (int p = p_begin; p < p_end; ++p, o += C) {
             // the mask is the same in every lane; the OR-reduction moves it to a uniform register so the
             // tests below are uniform branches (no divergence bookkeeping)
             const unsigned m = __reduce_or_sync(0xffffffffu, (unsigned)m_next);
-            m_next = sm.mask[p + 1];                                   // the array is padded by one
+            m_next = lds_i(a_mask + (p + 1) * 4);                     // the array is padded by one
             if (PREFETCH && (m & 0xF000u)) {
-                const int4 code = sm.code[p + WIDE_LOOKAHEAD];
+                const int4 code = lds_i4(a_code + (p + WIDE_LOOKAHEAD) * 16);
                 const int cvs[4] = {code.x, code.y, code.z, code.w};
 #pragma unroll
                 for (int v = 0; v < TILE_V; ++v) {
@@ -173,7 +199,7 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
 #endif
             if (m & 0xFFu) {
                 if (m & 0xF0u) {
-                    const int4 code = sm.code[p];
+                    const int4 code = lds_i4(a_code + p * 16);
                     if (m & 0x10u) D3F_WIDE_RELOAD(0, code.x)
                     if (m & 0x20u) D3F_WIDE_RELOAD(1, code.y)
                     if (m & 0x40u) D3F_WIDE_RELOAD(2, code.z)
@@ -194,12 +220,15 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
                 if (m & 8u) D3F_WIDE_FMA(3, wa1, wb1)
                 acc = make_float4(acc01.x, acc01.y, acc23.x, acc23.y);
 #else
-                // the weight reads of every visible view are issued before the first FMA
+                // the weight reads of every visible view are issued before the first FMA.  (Dispatching on the four
+                // visibility bits with a 16-way switch instead of this if-chain compiles to a compare tree, not an
+                // indexed branch, and measured 3 % slower: profiles/r02_experiment_switch_dispatch.jsonl.)
                 float4 w0, w1, w2, w3;
-                if (m & 1u) w0 = sm.w4[p * TILE_V + 0];
-                if (m & 2u) w1 = sm.w4[p * TILE_V + 1];
-                if (m & 4u) w2 = sm.w4[p * TILE_V + 2];
-                if (m & 8u) w3 = sm.w4[p * TILE_V + 3];
+                const unsigned aw = a_w4 + p * (TILE_V * 16);
+                if (m & 1u) w0 = lds_f4(aw);
+                if (m & 2u) w1 = lds_f4(aw + 16);
+                if (m & 4u) w2 = lds_f4(aw + 32);
+                if (m & 8u) w3 = lds_f4(aw + 48);
                 if (m & 1u) D3F_WIDE_FMA1(0, w0)
                 if (m & 2u) D3F_WIDE_FMA1(1, w1)
                 if (m & 4u) D3F_WIDE_FMA1(2, w2)
