@@ -442,7 +442,7 @@ def main():
     torch.cuda.synchronize(dev)
     # Keep the GPU under this load for ~0.5 s so nvidia-smi samples it.  The count is FIXED, never time-based: every
     # step contains a collective at N > 1, so all ranks must run exactly the same number of steps.
-    for _ in range(300):
+    for _ in range(int(os.environ.get('D3F_BENCH_LOAD_STEPS', '300'))):      # (shortened under ncu: a launch list of 600 warm-up kernels helps nobody)
         out = step()
         flush.zero_()
     torch.cuda.synchronize(dev)

@@ -2,6 +2,7 @@
 // launch.  No torch, no host-side math on tensors; every entry point is asynchronous on the
 // caller's stream except d3f_eval_host.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges cost nanoseconds when no profiler is attached
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -25,6 +26,12 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 thread_local const char* g_variant[D3F_MAX_KEYS] = {};
+
+// NVTX range around an entry point: shows up as d3f_* in Nsight Systems / ncu --nvtx timelines.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -332,6 +339,7 @@ int d3f_sizeof_obs(void) { return (int)sizeof(D3FObs); }
 int d3f_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys, int32_t n_keys,
              float* dist, uint8_t* valid, float* const* out, float* const* out_inter,
              uint32_t flags, float mu, void* stream) {
+    NvtxRange nvtx_("d3f_eval");
     int rc = validate(obs, pts, n, keys, n_keys, dist, valid, out, flags, mu);
     if (rc) return rc;
     if ((rc = check_device())) return rc;
@@ -342,6 +350,7 @@ int d3f_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys,
 int d3f_eval_host(const D3FObs* obs, const float* pts_host, int64_t n, const D3FKey* keys, int32_t n_keys,
                   float* dist_host, uint8_t* valid_host, float* const* out_host, uint32_t flags, float mu,
                   void* obs_stream) {
+    NvtxRange nvtx_("d3f_eval_host");
     int rc = validate(obs, pts_host, n, keys, n_keys, dist_host, valid_host, out_host, flags, mu);
     if (rc) return rc;
     if ((rc = check_device())) return rc;
@@ -398,6 +407,7 @@ int d3f_release_scratch(void) {
 int d3f_eval_ordered(const D3FObs* obs, const float* pts, int64_t n, const int32_t* order,
                      const D3FKey* keys, int32_t n_keys, float* dist, uint8_t* valid, float* const* out,
                      uint32_t flags, float mu, void* stream) {
+    NvtxRange nvtx_("d3f_eval_ordered");
     int rc = validate(obs, pts, n, keys, n_keys, dist, valid, out, flags, mu);
     if (rc) return rc;
     if (n > 0 && !order) return fail(D3F_EINVAL, "order is NULL");
@@ -411,6 +421,7 @@ int64_t d3f_bin_workspace_bytes(int64_t n) { return (int64_t)d3f::bin_workspace_
 
 int d3f_bin_order(const float* pts, int64_t n, float cell, int32_t* order, void* workspace, int64_t workspace_bytes,
                   void* stream) {
+    NvtxRange nvtx_("d3f_bin_order");
     if (n < 0 || n >= (1ll << 31)) return fail(D3F_EINVAL, "bin: n=%lld outside 0..2^31", (long long)n);
     if (n > 0 && (!pts || !order || !workspace)) return fail(D3F_EINVAL, "bin: NULL pointer");
     if (!(cell > 0.f)) return fail(D3F_EINVAL, "bin: cell=%g must be positive", (double)cell);
@@ -434,7 +445,9 @@ int d3f_bin_order(const float* pts, int64_t n, float cell, int32_t* order, void*
     d3f::bin_scan_kernel<<<d3f::BIN_SCAN_BLOCKS, d3f::BIN_SCAN_THREADS, 0, st>>>(hist, block_base);
     d3f::bin_scan_base_kernel<<<1, d3f::BIN_SCAN_BLOCKS, 0, st>>>(block_base);
     d3f::bin_scatter_kernel<<<blocks, d3f::BIN_THREADS, 0, st>>>(keys, n, hist, block_base, order);
-    g_launches.fetch_add(6, std::memory_order_relaxed);
+    static const bool refine = [] { const char* e = getenv("D3F_BIN_REFINE"); return e ? atoi(e) != 0 : true; }();
+    if (refine) d3f::bin_refine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pts, n, cell, bbox, order);
+    g_launches.fetch_add(refine ? 7 : 6, std::memory_order_relaxed);
     D3F_CUDA(cudaGetLastError());
     return D3F_OK;
 }
@@ -444,6 +457,7 @@ int d3f_sweep_select(const D3FObs* obs, const D3FGrid* grid, const float* pts, i
                      float* dist_out, uint8_t* valid_out,
                      int64_t capacity, int64_t* sel_count, int32_t* sel_index, int32_t* sel_inst,
                      uint32_t flags, float mu, void* stream) {
+    NvtxRange nvtx_("d3f_sweep_select");
     if (!obs) return fail(D3F_EINVAL, "obs is NULL");
     if (obs->V < 1 || obs->V > D3F_MAX_VIEWS) return fail(D3F_EINVAL, "V=%d outside 1..%d", obs->V, D3F_MAX_VIEWS);
     if (obs->H < 2 || obs->W < 2) return fail(D3F_EINVAL, "image size %dx%d must be at least 2x2", obs->H, obs->W);
@@ -574,6 +588,7 @@ int d3f_eval_allgather(D3FComm* c, const D3FObs* obs, const float* pts, int64_t 
                        const D3FKey* keys, int32_t n_keys, float* const* out,
                        int64_t gather_base, int64_t gather_block, int64_t gather_stride,
                        uint32_t flags, float mu, void* stream, float** dist_all, uint8_t** valid_all) {
+    NvtxRange nvtx_("d3f_eval_allgather");
     if (!c || !c->connected) return fail(D3F_EINVAL, "comm is NULL or not connected");
     int rc = validate(obs, pts, n, keys, n_keys, nullptr, nullptr, out, flags, mu, false);
     if (rc) return rc;
@@ -604,6 +619,7 @@ int d3f_eval_allgather(D3FComm* c, const D3FObs* obs, const float* pts, int64_t 
 }
 
 int d3f_comm_broadcast(D3FComm* c, void* buf, int64_t bytes, int32_t root, void* stream) {
+    NvtxRange nvtx_("d3f_comm_broadcast");
     if (!c || !c->connected) return fail(D3F_EINVAL, "comm is NULL or not connected");
     if (root < 0 || root >= c->world) return fail(D3F_EINVAL, "broadcast: root %d outside 0..%d", root, c->world - 1);
     if (bytes < 0 || (bytes > 0 && !buf)) return fail(D3F_EINVAL, "broadcast: bad buffer");
@@ -642,6 +658,7 @@ int d3f_comm_broadcast(D3FComm* c, void* buf, int64_t bytes, int32_t root, void*
 int d3f_eval_backward(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys, int32_t n_keys,
                       const float* const* grad_out, const float* grad_dist, float* grad_pts,
                       uint32_t flags, float mu, void* stream) {
+    NvtxRange nvtx_("d3f_eval_backward");
     if (!obs) return fail(D3F_EINVAL, "obs is NULL");
     if (obs->V < 1 || obs->V > D3F_MAX_VIEWS) return fail(D3F_EINVAL, "V=%d outside 1..%d", obs->V, D3F_MAX_VIEWS);
     if (obs->H < 2 || obs->W < 2) return fail(D3F_EINVAL, "image size %dx%d must be at least 2x2", obs->H, obs->W);
@@ -684,6 +701,7 @@ int d3f_eval_backward(const D3FObs* obs, const float* pts, int64_t n, const D3FK
 
 int d3f_pca_project(const float* x, int64_t n, int32_t C, const float* mean, const float* components,
                     int32_t n_comp, float* y, void* stream) {
+    NvtxRange nvtx_("d3f_pca_project");
     if (n < 0 || C < 1 || n_comp < 1 || n_comp > d3f::PCA_MAX_COMP)
         return fail(D3F_EINVAL, "pca: n=%lld C=%d n_comp=%d (n_comp must be 1..%d)", (long long)n, C, n_comp, d3f::PCA_MAX_COMP);
     if (n > 0 && (!x || !components || !y)) return fail(D3F_EINVAL, "pca: NULL pointer");
@@ -702,6 +720,7 @@ int d3f_pca_project(const float* x, int64_t n, int32_t C, const float* mean, con
 
 int d3f_create_grid(double x_lower, double y_lower, double z_lower, double step,
                     int32_t nx, int32_t ny, int32_t nz, float* pts, void* stream) {
+    NvtxRange nvtx_("d3f_create_grid");
     if (nx < 0 || ny < 0 || nz < 0) return fail(D3F_EINVAL, "grid: negative size");
     const int64_t n = (int64_t)nx * ny * nz;
     if (n > 0 && !pts) return fail(D3F_EINVAL, "grid: pts is NULL");

@@ -144,6 +144,60 @@ bin_scan_base_kernel(uint32_t* __restrict__ block_base) {
     block_base[t] = base + inc - v;
 }
 
+__device__ __forceinline__ unsigned spread3_10(unsigned v) {   // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// Second level: inside every aligned block of 256 positions of `order` (= one tile of the ordered field kernel) sort
+// by a Morton key eight times finer per axis than the lattice (30 bits).  The lattice bins hold ~10 points in no
+// particular order; after this pass consecutive points of a tile are nearest neighbours along the z-curve, so the walk
+// re-enters a texel cell far less often (measured: L2->L1 read sectors of the walk, profiles/r02_binned*_summary.txt).
+// One CTA per block, bitonic sort in shared memory.
+constexpr int BIN_FINE_BITS = BIN_BITS + 3;
+__global__ void __launch_bounds__(256)
+bin_refine_kernel(const float* __restrict__ pts, int64_t n, float cell, const int* __restrict__ bbox,
+                  int32_t* __restrict__ order) {
+    __shared__ unsigned long long kv[256];
+    const int t = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * 256 + t;
+    unsigned long long e = ~0ull;                       // padding sorts to the end
+    if (i < n) {
+        const int row = order[i];
+        const int side = 1 << BIN_BITS, fine = 1 << BIN_FINE_BITS;
+        unsigned q[3];
+        bool ok = true;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float lo = ordered_to_float(bbox[a]), hi = ordered_to_float(bbox[3 + a]);
+            const float c = fmaxf(cell, (hi - lo) / (float)side * 1.0001f) * 0.125f;
+            const float f = __ldg(pts + (size_t)row * 3 + a);
+            ok = ok && isfinite(f);
+            q[a] = (unsigned)min(max((int)floorf((f - lo) / c), 0), fine - 1);
+        }
+        const unsigned key = ok ? ((spread3_10(q[0]) << 2) | (spread3_10(q[1]) << 1) | spread3_10(q[2])) : 0x3fffffffu;
+        e = ((unsigned long long)key << 32) | (unsigned)row;
+    }
+    kv[t] = e;
+    __syncthreads();
+    for (int k = 2; k <= 256; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int partner = t ^ j;
+            if (partner > t) {
+                const unsigned long long a = kv[t], b = kv[partner];
+                const bool up = (t & k) == 0;
+                if ((a > b) == up) { kv[t] = b; kv[partner] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (i < n) order[i] = (int32_t)(unsigned)(kv[t] & 0xffffffffu);
+}
+
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_scatter_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ cursor,
                    const uint32_t* __restrict__ block_base, int32_t* __restrict__ order) {

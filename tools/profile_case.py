@@ -5,7 +5,8 @@
         -o gpurun_out/r02_visible python tools/profile_case.py visible
 
 cases: grid (cfg2a), visible (1M grid points some view sees), none (1M points no view sees), scattered, binned
-(scattered walked in bin order, order precomputed), cfg5 (256k keypoints), sweep (101.9M-point select), backward.
+(scattered walked in bin order, order precomputed), cfg5 (256k keypoints), sweep (101.9M-point select), backward,
+pca (eval_pca on 256k keypoints), dist16m (dist/valid only, 16M grid points), mask (cfg3: u8 instance-mask field).
 """
 import os
 import sys
@@ -49,6 +50,25 @@ def main():
             r = f.sweep_select(b, 0.001)
         torch.cuda.synchronize()
         print(case, r['count'])
+        return
+    elif case == 'pca':
+        pts = torch.from_numpy(S.scattered_points(262144, 0)).to(DEV)
+        comp = torch.randn(3, 1024, device=DEV); mean = torch.randn(1024, device=DEV)
+        for _ in range(reps):
+            r = f.eval_pca(pts, 'dino_feats', mean, comp)
+        torch.cuda.synchronize()
+        return
+    elif case == 'dist16m':
+        pts = torch.from_numpy(S.grid_points(400, 200, 200)).to(DEV)
+        for _ in range(reps):
+            r = f.eval(pts, [])
+        torch.cuda.synchronize()
+        return
+    elif case == 'mask':
+        pts = torch.from_numpy(S.config_points('cfg2a')).to(DEV)
+        for _ in range(reps):
+            r = f.eval(pts, ['mask'])
+        torch.cuda.synchronize()
         return
     elif case == 'backward':
         pts = torch.from_numpy(S.scattered_points(262144, 0)).to(DEV)
