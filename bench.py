@@ -492,6 +492,32 @@ def main():
         if not flag.item():
             sys.stderr.write(f'rank {rank}: gathered field differs from the single-rank evaluation: {parity}\n')
 
+    # ---- N > 1: what the remaining inefficiency is made of (outside the timed region) -----------------------------------
+    breakdown = None
+    if world > 1:
+        def timed_ms(fn, reps=10):
+            fn(); fn()
+            torch.cuda.synchronize(dev)
+            ts = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                flush.zero_()
+                torch.cuda.synchronize(dev)
+                ts.append(a.elapsed_time(b))
+            return float(np.median(ts))
+        local_ms = timed_ms(lambda: f.eval(share.local, return_names=names))        # same points, no exchange, no peers
+        dist.barrier()
+        shard_ms = timed_ms(step)
+        t = torch.tensor([local_ms, shard_ms], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        loc = [float(x[0]) for x in allt]
+        shd = [float(x[1]) for x in allt]
+        breakdown = {'local_kernel_ms_per_rank': loc, 'sharded_step_ms_per_rank': shd,
+                     'rank_skew_ms': max(loc) - min(loc), 'exchange_overhead_ms': max(shd) - max(loc),
+                     'what': 'median of 10: the rank\'s share evaluated alone (no gather) vs the sharded step; the step costs the slowest rank plus the flag exchange'}
+
     # ---- end to end: host points in, host results out, through the public API --------------------------
     e2e = None
     if not args.no_e2e:
@@ -585,6 +611,7 @@ def main():
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
         'clocks': clk.summary(), 'wall_s_timed_region': t_wall, 'step_ms_min': float(min(step_ms)),
         'step_ms_max': float(max(step_ms)), 'checksum': checksum, 'multi_gpu_parity': parity,
+        'multi_gpu_breakdown': breakdown,
     }
     line.update(extras)
     print(json.dumps(line), flush=True)
