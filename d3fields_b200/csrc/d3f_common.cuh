@@ -95,15 +95,21 @@ __device__ __forceinline__ void store_compact(const EvalParams& ep, int64_t i, f
     }
 }
 
-// End of a gathering launch, called by every thread of every CTA.  The CTA's remote stores are ordered before its
-// arrival (bar.sync, then fence.sys by thread 0: cumulative); the last CTA to arrive publishes this rank's epoch to
-// every peer and waits until every peer has published the same epoch, so when the launch completes the local
+// End of a gathering launch, called by every thread of every CTA.
+//
+// Ordering (PTX memory model, fences are cumulative): a CTA's remote stores are ordered before its arrival on the
+// launch counter by bar.sync + a GPU-scope fence of thread 0 + a GPU-scope atomic; the last CTA to arrive has thereby
+// observed every CTA's stores, and ITS system-scope fence followed by release stores of the epoch flags orders all of
+// them before the flags for the peers.  Only one system-scope fence per launch: a fence.sys costs a round trip through
+// the NVLink fabric (~4 us measured), and one per CTA cost 0.10-0.13 ms per step on 2M points (8 % — profiles/
+// r02_bench_n8_fence_sys_per_cta.json); the GPU-scope fence is satisfied at the local L2.
+// The last CTA then waits until every peer has published the same epoch, so when the launch completes the local
 // gathered arrays hold all ranks' results.
 __device__ __forceinline__ void gather_epilogue(const EvalParams& ep) {
     if (ep.g.world == 0) return;
     __syncthreads();
     if (threadIdx.x != 0) return;
-    __threadfence_system();
+    __threadfence();
     const unsigned arrived = atomicAdd(ep.g.counter, 1u);
     if (arrived != gridDim.x - 1) return;
     *ep.g.counter = 0;                               // the next launch on this stream starts from zero
