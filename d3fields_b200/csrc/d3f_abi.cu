@@ -110,28 +110,27 @@ int validate(const D3FObs* obs, const void* pts, int64_t n, const D3FKey* keys, 
 // Device-pointer evaluation shared by d3f_eval and the slabs of d3f_eval_host.
 __global__ void gather_only_kernel(const d3f::EvalParams ep) { d3f::gather_epilogue(ep); }
 
-template <bool RECIP, int VARIANT, bool WIDE, bool ORDERED>
-cudaError_t launch_tile_inst(dim3 grid, dim3 block, cudaStream_t st, const d3f::EvalParams& ep, const d3f::KeySet& ks) {
-    constexpr size_t smem = d3f::WALK_FFMA2 ? sizeof(d3f::TileSmemT<WIDE>) : 0;      // static shared memory otherwise
-    // once per instantiation and device: the wide tile needs more than the default 48 KB of dynamic shared memory
-    static std::atomic<uint64_t> opted{0};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (smem > 48 * 1024 && !(opted.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
-        e = cudaFuncSetAttribute(d3f::field_tile_kernel<RECIP, VARIANT, WIDE, ORDERED>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        opted.fetch_or(1ull << (dev & 63), std::memory_order_release);
-    }
-    d3f::field_tile_kernel<RECIP, VARIANT, WIDE, ORDERED><<<grid, block, smem, st>>>(ep, ks);
-    return cudaSuccess;
+template <bool RECIP, int VARIANT, bool WIDE, int NV>
+void launch_tile(bool ordered, dim3 grid, dim3 block, cudaStream_t st, const d3f::EvalParams& ep, const d3f::KeySet& ks) {
+    if (ordered) d3f::field_tile_kernel<RECIP, VARIANT, WIDE, true, NV><<<grid, block, 0, st>>>(ep, ks);
+    else         d3f::field_tile_kernel<RECIP, VARIANT, WIDE, false, NV><<<grid, block, 0, st>>>(ep, ks);
 }
 
-template <bool RECIP, int VARIANT, bool WIDE>
-cudaError_t launch_tile(bool ordered, dim3 grid, dim3 block, cudaStream_t st, const d3f::EvalParams& ep, const d3f::KeySet& ks) {
-    return ordered ? launch_tile_inst<RECIP, VARIANT, WIDE, true>(grid, block, st, ep, ks)
-                   : launch_tile_inst<RECIP, VARIANT, WIDE, false>(grid, block, st, ep, ks);
+// NV = 4: up to four views (every configuration the reference runs).  NV = 8: five to eight views; the lookahead
+// prefetch variant is not instantiated there.
+template <int NV>
+void launch_tile_nv(bool recip, bool wide, bool prefetch, bool ordered, dim3 grid, dim3 block, cudaStream_t st,
+                    const d3f::EvalParams& ep, const d3f::KeySet& ks) {
+    if (!wide) {                        // no register-cached walk needed: the light instantiation (4 CTAs/SM)
+        if (recip) launch_tile<true, 0, false, NV>(ordered, grid, block, st, ep, ks);
+        else       launch_tile<false, 0, false, NV>(ordered, grid, block, st, ep, ks);
+    } else if (NV == 4 && prefetch) {
+        if (recip) launch_tile<true, 4, true, 4>(ordered, grid, block, st, ep, ks);
+        else       launch_tile<false, 4, true, 4>(ordered, grid, block, st, ep, ks);
+    } else {
+        if (recip) launch_tile<true, 0, true, NV>(ordered, grid, block, st, ep, ks);
+        else       launch_tile<false, 0, true, NV>(ordered, grid, block, st, ep, ks);
+    }
 }
 
 int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys, int32_t n_keys,
@@ -175,16 +174,20 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
         }
         g_variant[k] = "generic";
     }
-    // production path: 128-point tiles, register-cached corner texels for wide float32 maps
+    // production path: point tiles, register-cached corner texels for wide float32 maps
+    const int nv = obs->V <= 4 ? 4 : 8;
+    const int slice = nv == 4 ? d3f::TileGeom<4>::SLICE : d3f::TileGeom<8>::SLICE;
+    const int tile_pts = nv == 4 ? d3f::TileGeom<4>::PTS : d3f::TileGeom<8>::PTS;
     auto is_wide = [&](int k) {
-        return d3f::key_is_wide(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w, ks.k[k].sv, ks.k[k].sy, ks.k[k].sx);
+        return d3f::key_is_wide(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w, ks.k[k].sv, ks.k[k].sy, ks.k[k].sx, slice);
     };
-    bool tile_ok = obs->V <= d3f::TILE_V && !any_inter;
+    static const bool force_generic = [] { const char* e = getenv("D3F_FORCE_GENERIC"); return e && atoi(e) != 0; }();   // A/B only
+    bool tile_ok = obs->V <= d3f::TILE_MAX_V && !any_inter && !force_generic;
     for (int k = 0; k < ks.n_keys; ++k)
-        tile_ok &= d3f::key_fits_tile(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w, ks.k[k].sv, ks.k[k].sy, ks.k[k].sx);
+        tile_ok &= d3f::key_fits_tile(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w, ks.k[k].sv, ks.k[k].sy, ks.k[k].sx, slice);
     if (any_inter && order) return fail(D3F_EINVAL, "per-view outputs are not available on an ordered launch");
     if (tile_ok) {
-        const int64_t tiles = (n + d3f::TILE_PTS - 1) / d3f::TILE_PTS;
+        const int64_t tiles = (n + tile_pts - 1) / tile_pts;
         if (tiles > 0x7fffffffll) return fail(D3F_EINVAL, "n=%lld too large for one launch", (long long)n);
         for (int k = 0; k < ks.n_keys; ++k)
             g_variant[k] = is_wide(k) ? "tile/wide" : "tile/narrow";
@@ -196,19 +199,8 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
         for (int k = 0; k < ks.n_keys; ++k)
             if (is_wide(k)) wide_bytes += (size_t)obs->V * keys[k].h * keys[k].w * keys[k].C * 4;
         const bool prefetch = force >= 0 ? force != 0 : wide_bytes > (size_t)(64u << 20);
-        const bool ord = order != nullptr;
-        cudaError_t le;
-        if (wide_bytes == 0) {            // no register-cached walk needed: the light instantiation (4 CTAs/SM)
-            le = recip ? launch_tile<true, 0, false>(ord, grid, block, st, ep, ks)
-                       : launch_tile<false, 0, false>(ord, grid, block, st, ep, ks);
-        } else if (recip) {
-            le = prefetch ? launch_tile<true, 4, true>(ord, grid, block, st, ep, ks)
-                          : launch_tile<true, 0, true>(ord, grid, block, st, ep, ks);
-        } else {
-            le = prefetch ? launch_tile<false, 4, true>(ord, grid, block, st, ep, ks)
-                          : launch_tile<false, 0, true>(ord, grid, block, st, ep, ks);
-        }
-        if (le != cudaSuccess) return fail(D3F_ECUDA, "tile kernel launch setup failed: %s", cudaGetErrorString(le));
+        if (nv == 4) launch_tile_nv<4>(recip, wide_bytes != 0, prefetch, order != nullptr, grid, block, st, ep, ks);
+        else         launch_tile_nv<8>(recip, wide_bytes != 0, prefetch, order != nullptr, grid, block, st, ep, ks);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         D3F_CUDA(cudaGetLastError());
         return D3F_OK;

@@ -1,6 +1,6 @@
-// d3f_tile.cuh — the production field-query kernel (V <= 4, no per-view outputs).
+// d3f_tile.cuh — the production field-query kernel (V <= 8, no per-view outputs).
 //
-// One CTA (256 threads) evaluates a tile of TILE_PTS = 256 consecutive query points:
+// One CTA (256 threads) evaluates a tile of consecutive query points (256 for up to 4 views, 128 for 5-8 views):
 //
 //   phase 0/1/1r  as in d3f_generic.cuh: H = [K@Rt;0001], one thread per (point, view) for
 //                 projection / nearest depth / visibility / distance weight, then one thread per
@@ -9,21 +9,25 @@
 //                 on that key's map: four corner weights already multiplied by the view factor
 //                 weight/(count+1e-6), and one packed code (north-west texel offset, east/south
 //                 step bits; -1 when the view does not see the point)
-//   wide maps     (float32, C % 128 == 0, e.g. the 1024-channel DINOv2 volume): a warp owns a
-//                 128-channel slice (one float4 per lane) and marches over the tile's points in
+//   wide maps     (float32, C a multiple of the slice width, e.g. the 1024-channel DINOv2 volume): a warp owns a
+//                 channel slice (128 channels = one float4 per lane for NV = 4; 64 channels = one float2 per lane for
+//                 NV = 8, so that the cache below stays 64 registers) and marches over the tile's points in
 //                 order.  The four corner texels of each view stay in registers and are reloaded
 //                 only when the packed code changes — neighbouring grid points project into the
 //                 same texel cell most of the time, so the 16 KB-per-point gather of the reference
 //                 (4 views x 4 corners x C floats) collapses to a reload every few points, served
 //                 by L1/L2 (the whole volume is L2-resident).  Per visible view the inner loop is
-//                 one 128-bit shared-memory read of the folded weights and 16 FFMA per lane; the
-//                 output row is written once with 128-bit streaming stores (st.global.cs), 512
-//                 contiguous bytes per warp, so the 4 KB/point output stream never evicts the
-//                 feature volume from L2.
+//                 one 128-bit shared-memory read of the folded weights and 4 FFMA per channel; the
+//                 output row is written once with streaming stores (st.global.cs), a contiguous slice per warp,
+//                 so the 4 KB/point output stream never evicts the feature volume from L2.
 //   narrow maps   (instance masks, colours; u8 or f32, any C): threads sweep (point, channel-group).
 //
 // HBM traffic is the algorithmic minimum: points and depth pixels in, each output byte out once; the
 // feature volume is read from HBM once and then lives in L2.
+//
+// Experiments on this walk that were measured and rejected (packed FFMA2 accumulation, strided tile order, switch
+// dispatch, unconditional weight reads, TMEM-resident cache, TMA stores, ...) are listed with their numbers in DESIGN.md
+// 4.7 / 4.8; their sources are under profiles/patches/.
 #pragma once
 #include "d3f_common.cuh"
 #include "d3f_generic.cuh"
@@ -31,52 +35,75 @@
 namespace d3f {
 
 constexpr int TILE_THREADS = 256;
-constexpr int TILE_PTS = 256;            // measured: 256-point tiles beat 128 by 4 % (half the barriers and cold starts per point)
-constexpr int TILE_V = 4;             // views supported by this kernel (slots are padded to 4)
+constexpr int TILE_MAX_V = 8;            // views the tile kernel handles (more: field_generic_kernel)
 
-// D3F_WALK_FFMA2=1 builds the wide walk with packed FFMA2 accumulation (two channels per instruction, weights stored
-// twice in shared memory, 60 KB dynamic shared memory).  Measured on B200 (profiles/r02_experiment_ffma2.jsonl):
-// bit-identical results, 1.5 % SLOWER on cfg2a and 4 % slower on a fully visible grid — the FP32 pipe is not what
-// limits the walk, and the second LDS.128 per view costs more than the 8 saved issue slots.  Kept for A/B only.
-#ifndef D3F_WALK_FFMA2
-#define D3F_WALK_FFMA2 0
-#endif
-constexpr bool WALK_FFMA2 = D3F_WALK_FFMA2 != 0;
+// Geometry of a tile for NV view slots (4 or 8; a launch with V views uses the smallest NV >= V).
+template <int NV>
+struct TileGeom {
+    static_assert(NV == 4 || NV == 8, "view slots per point: 4 or 8");
+    static constexpr int PTS = NV == 4 ? 256 : 128;      // 256-point tiles beat 128 by 4 % at NV = 4 (fewer barriers and cold starts)
+    static constexpr int LOG_NV = NV == 4 ? 2 : 3;
+    static constexpr int LANE_CH = NV == 4 ? 4 : 2;      // channels per lane: the register cache is NV x 4 corners x LANE_CH = 64
+    static constexpr int SLICE = 32 * LANE_CH;           // channels a warp owns
+    static constexpr int CHG = NV;                       // mask bits [0,NV): view sees the point; [NV,2NV): its cell changed
+    static constexpr int AHEAD = NV == 4 ? 12 : 16;      // [AHEAD, AHEAD+NV): cell change WIDE_LOOKAHEAD points further on
+    static constexpr unsigned VIEWS = (1u << NV) - 1u;
+};
+constexpr int TILE_PTS = TileGeom<4>::PTS;
 
-template <bool WIDE>
+template <bool WIDE, int NV>
 struct TileSmemT {
-    float H[TILE_V * 12];
-    float px[TILE_PTS * TILE_V];
-    float py[TILE_PTS * TILE_V];
-    float d[TILE_PTS * TILE_V];
-    float fac[TILE_PTS * TILE_V];
-    int vis[TILE_PTS * TILE_V];
-    float4 w4[TILE_PTS * TILE_V * ((WIDE && WALK_FFMA2) ? 2 : 1)];
-                                      // folded corner weights per (point, view).  Narrow keys: slot s holds (w_nw, w_ne, w_sw, w_se).
-                                      // Wide keys under D3F_WALK_FFMA2: slots 2s, 2s+1 hold every weight twice,
-                                      // (nw,nw,ne,ne) (sw,sw,se,se) — the operand layout of the packed FFMA2
-    int4 code[TILE_PTS + 4];          // packed footprint codes of the 4 views of a point: element offset of the
+    static constexpr int PTS = TileGeom<NV>::PTS;
+    float H[NV * 12];
+    float px[PTS * NV];
+    float py[PTS * NV];
+    float d[PTS * NV];
+    float fac[PTS * NV];
+    int vis[PTS * NV];
+    float4 w4[PTS * NV];              // folded corner weights per (point, view): (w_nw, w_ne, w_sw, w_se)
+    int code[(PTS + 4) * NV];         // packed footprint codes of the NV views of a point: element offset of the
                                       // north-west texel inside the view (wide maps: a multiple of 4, used as is;
                                       // narrow maps: shifted left by 2) | east-step bit | south-step bit << 1; -1 = unseen
-    int64_t row[TILE_PTS];            // output row of each point of the tile (ordered launches only)
-    int mask[TILE_PTS + 4];           // bits 0-3: view sees the point; bits 4-7: its corner cell differs from
-                                      // the previous point's (or the previous point did not see it);
-                                      // bits 12-15: bits 4-7 of the point WIDE_LOOKAHEAD further on in the same run
+    int64_t row[PTS];                 // output row of each point of the tile (ordered launches only)
+    int mask[PTS + 4];                // see TileGeom: visibility bits, cell-change bits, lookahead bits
 };
 
-// Texel loads: read-only path, kept in L1 with evict-last priority — the next cell a walk enters shares two of its
-// four corners with the current one, and the output stream must not push them out (measured -1 %).
-__device__ __forceinline__ float4 ldg4(const float* p) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
+// The lane's slice of one texel / one output row: float4 (NV = 4) or float2 (NV = 8).
+template <int LANE_CH> struct LaneVec;
+template <> struct LaneVec<4> {
+    using type = float4;
+    static __device__ __forceinline__ type zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    // Texel loads: read-only path, kept in L1 with evict-last priority — the next cell a walk enters shares two of its
+    // four corners with the current one, and the output stream must not push them out (measured -1 %).
+    static __device__ __forceinline__ type ldg(const float* p) {
+        float4 r;
+        asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+        return r;
+    }
+    static __device__ __forceinline__ void fma(type& a, float w, const type& f) {
+        a.x = fmaf(w, f.x, a.x); a.y = fmaf(w, f.y, a.y); a.z = fmaf(w, f.z, a.z); a.w = fmaf(w, f.w, a.w);
+    }
+    static __device__ __forceinline__ void stcs(float* p, const type& v) { __stcs(reinterpret_cast<float4*>(p), v); }
+};
+template <> struct LaneVec<2> {
+    using type = float2;
+    static __device__ __forceinline__ type zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ type ldg(const float* p) {
+        float2 r;
+        asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+        return r;
+    }
+    static __device__ __forceinline__ void fma(type& a, float w, const type& f) {
+        a.x = fmaf(w, f.x, a.x); a.y = fmaf(w, f.y, a.y);
+    }
+    static __device__ __forceinline__ void stcs(float* p, const type& v) { __stcs(reinterpret_cast<float2*>(p), v); }
+};
 
 // Shared-memory reads of the walk go through explicit 32-bit shared addresses that are computed ONCE per walk and
 // pinned in a register (the opaque mov): left to itself the compiler re-derives the CTA's shared-window base
 // (S2UR SR_CgaCtaId + ULEA) in front of every point's weight reads, which puts a special-register read at the head of
-// each point's dependency chain.
+// each point's dependency chain (measured: cfg2a 0.781 -> 0.760 ms, fully visible grid 1.075 -> 1.022 ms).
 __device__ __forceinline__ unsigned smem_addr(const void* p) {
     unsigned a = (unsigned)__cvta_generic_to_shared(p), r;
     asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
@@ -98,52 +125,33 @@ __device__ __forceinline__ int lds_i(unsigned a) {
     return r;
 }
 
-// Number of point runs a tile is split into for a map of S 128-channel slices (8 warps per CTA).
-__host__ __device__ inline int wide_runs(int S) { return S >= TILE_THREADS / 32 ? 1 : (TILE_THREADS / 32) / S; }
-__host__ __device__ inline int wide_run_len(int S) { const int R = wide_runs(S); return (TILE_PTS + R - 1) / R; }
+// The NV packed codes of point p (shared address a_code), as registers.
+template <int NV>
+__device__ __forceinline__ void load_codes(unsigned a_code, int p, int (&cv)[NV]) {
+    const int4 c0 = lds_i4(a_code + p * (NV * 4));
+    cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w;
+    if constexpr (NV == 8) {
+        const int4 c1 = lds_i4(a_code + p * (NV * 4) + 16);
+        cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+    }
+}
 
-// Reload the four corner texels of view v (lane's 4 channels) from the packed footprint code.
-// 32-bit element offsets: a view's map holds fewer than 2^31 elements (checked on the host).
-#define D3F_WIDE_RELOAD(v, cv)                                                                     \
-    {                                                                                              \
-        const float* b_ = vbase[v] + (unsigned)((cv) & ~3);                                        \
-        const unsigned dx_ = ((cv) & 1) ? (unsigned)kp.sx : 0u;                                    \
-        const unsigned dy_ = ((cv) & 2) ? (unsigned)kp.sy : 0u;                                    \
-        cc[v][0] = ldg4(b_); cc[v][1] = ldg4(b_ + dx_);                                            \
-        cc[v][2] = ldg4(b_ + dy_); cc[v][3] = ldg4(b_ + (dy_ + dx_));                              \
-    }
-// acc (4 channels) += w_corner * texel_corner for the four corners of view v, two channels per FFMA2.
-// sm_100 issues a 3-register FFMA every other cycle per scheduler; the packed form carries two FMAs per issue, which
-// is what lets a fully visible tile run at the HBM rate instead of the FP32 pipe's (measured: DESIGN.md §4.8).
-// Per channel the order of the additions is the same as the scalar form's: nw, ne, sw, se — results are bit-identical.
-#define D3F_WIDE_FMA1(v, w_)                                                                       \
-    {                                                                                              \
-        fma4(acc, w_.x, cc[v][0]); fma4(acc, w_.y, cc[v][1]);                                      \
-        fma4(acc, w_.z, cc[v][2]); fma4(acc, w_.w, cc[v][3]);                                      \
-    }
-#define D3F_WIDE_FMA(v, wa_, wb_)                                                                  \
-    {                                                                                              \
-        const float2 w0_ = make_float2(wa_.x, wa_.y), w1_ = make_float2(wa_.z, wa_.w);             \
-        const float2 w2_ = make_float2(wb_.x, wb_.y), w3_ = make_float2(wb_.z, wb_.w);             \
-        acc01 = __ffma2_rn(make_float2(cc[v][0].x, cc[v][0].y), w0_, acc01);                       \
-        acc23 = __ffma2_rn(make_float2(cc[v][0].z, cc[v][0].w), w0_, acc23);                       \
-        acc01 = __ffma2_rn(make_float2(cc[v][1].x, cc[v][1].y), w1_, acc01);                       \
-        acc23 = __ffma2_rn(make_float2(cc[v][1].z, cc[v][1].w), w1_, acc23);                       \
-        acc01 = __ffma2_rn(make_float2(cc[v][2].x, cc[v][2].y), w2_, acc01);                       \
-        acc23 = __ffma2_rn(make_float2(cc[v][2].z, cc[v][2].w), w2_, acc23);                       \
-        acc01 = __ffma2_rn(make_float2(cc[v][3].x, cc[v][3].y), w3_, acc01);                       \
-        acc23 = __ffma2_rn(make_float2(cc[v][3].z, cc[v][3].w), w3_, acc23);                       \
-    }
+// Number of point runs a tile is split into for a map of S channel slices (8 warps per CTA).
+__host__ __device__ inline int wide_runs(int S) { return S >= TILE_THREADS / 32 ? 1 : (TILE_THREADS / 32) / S; }
+__host__ __device__ inline int wide_run_len(int S, int pts) { const int R = wide_runs(S); return (pts + R - 1) / R; }
 
 constexpr int WIDE_LOOKAHEAD = 4;      // points between the L1 prefetch of a cell change and its reload
 
-// PREFETCH: bits 12-15 of a point's mask word say which views change cell WIDE_LOOKAHEAD points later; the warp
-// then prefetches its own 512-byte slice of those corner texels into L1, so the reload that follows is an L1 hit
+// PREFETCH: the lookahead bits of a point's mask word say which views change cell WIDE_LOOKAHEAD points later; the warp
+// then prefetches its own slice of those corner texels into L1, so the reload that follows is an L1 hit
 // instead of an L2 round trip with all eight warps of the CTA stalled on the same point.
-template <bool PREFETCH, bool ORDERED>
-__device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<true>& sm) {
+template <bool PREFETCH, bool ORDERED, int NV>
+__device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<true, NV>& sm) {
+    using G = TileGeom<NV>;
+    using LV = LaneVec<G::LANE_CH>;
+    using vec = typename LV::type;
     const int C = kp.C;
-    const int S = C >> 7;                                   // 128-channel slices
+    const int S = C / G::SLICE;                             // channel slices
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = TILE_THREADS / 32;
     int s0, sstep, p_begin, p_end;
@@ -152,7 +160,7 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
     } else {                                                // fewer slices than warps: split the tile into runs
         const int r = warp / S;
         if (r >= wide_runs(S)) return;
-        const int run = wide_run_len(S);
+        const int run = wide_run_len(S, G::PTS);
         s0 = warp - r * S; sstep = S;
         p_begin = r * run; p_end = min(p_begin + run, npts);
     }
@@ -160,32 +168,31 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
     const float* __restrict__ vol = static_cast<const float*>(kp.data);
     const unsigned a_mask = smem_addr(sm.mask), a_code = smem_addr(sm.code), a_w4 = smem_addr(sm.w4);
     for (int s = s0; s < S; s += sstep) {
-        const float* vbase[TILE_V];
+        const float* vbase[NV];
 #pragma unroll
-        for (int v = 0; v < TILE_V; ++v) vbase[v] = vol + (size_t)v * (size_t)kp.sv + s * 128 + lane * 4;
-        float* o = kp.out + (size_t)(tile0 + p_begin) * C + s * 128 + lane * 4;
-        float* const o_col = kp.out + s * 128 + lane * 4;
-        float4 cc[TILE_V][4];
+        for (int v = 0; v < NV; ++v) vbase[v] = vol + (size_t)v * (size_t)kp.sv + s * G::SLICE + lane * G::LANE_CH;
+        float* o = kp.out + (size_t)(tile0 + p_begin) * C + s * G::SLICE + lane * G::LANE_CH;
+        float* const o_col = kp.out + s * G::SLICE + lane * G::LANE_CH;
+        vec cc[NV][4];
 #pragma unroll
-        for (int v = 0; v < TILE_V; ++v)
+        for (int v = 0; v < NV; ++v)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cc[v][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < 4; ++q) cc[v][q] = LV::zero();
         int m_next = lds_i(a_mask + p_begin * 4);
         for (int p = p_begin; p < p_end; ++p, o += C) {
             // the mask is the same in every lane; the OR-reduction moves it to a uniform register so the
             // tests below are uniform branches (no divergence bookkeeping)
             const unsigned m = __reduce_or_sync(0xffffffffu, (unsigned)m_next);
             m_next = lds_i(a_mask + (p + 1) * 4);                     // the array is padded by one
-            if (PREFETCH && (m & 0xF000u)) {
-                const int4 code = lds_i4(a_code + (p + WIDE_LOOKAHEAD) * 16);
-                const int cvs[4] = {code.x, code.y, code.z, code.w};
+            if (PREFETCH && ((m >> G::AHEAD) & G::VIEWS)) {
+                int cv[NV];
+                load_codes<NV>(a_code, p + WIDE_LOOKAHEAD, cv);
 #pragma unroll
-                for (int v = 0; v < TILE_V; ++v) {
-                    if (m & (0x1000u << v)) {
-                        const int cv = cvs[v];
-                        const float* b_ = vbase[v] + (unsigned)(cv & ~3);
-                        const unsigned dx_ = (cv & 1) ? (unsigned)kp.sx : 0u;
-                        const unsigned dy_ = (cv & 2) ? (unsigned)kp.sy : 0u;
+                for (int v = 0; v < NV; ++v) {
+                    if (m & (1u << (G::AHEAD + v))) {
+                        const float* b_ = vbase[v] + (unsigned)(cv[v] & ~3);
+                        const unsigned dx_ = (cv[v] & 1) ? (unsigned)kp.sx : 0u;
+                        const unsigned dy_ = (cv[v] & 2) ? (unsigned)kp.sy : 0u;
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(b_));
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(b_ + dx_));
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(b_ + dy_));
@@ -193,71 +200,62 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
                     }
                 }
             }
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#if D3F_WALK_FFMA2
-            float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
-#endif
-            if (m & 0xFFu) {
-                if (m & 0xF0u) {
-                    const int4 code = lds_i4(a_code + p * 16);
-                    if (m & 0x10u) D3F_WIDE_RELOAD(0, code.x)
-                    if (m & 0x20u) D3F_WIDE_RELOAD(1, code.y)
-                    if (m & 0x40u) D3F_WIDE_RELOAD(2, code.z)
-                    if (m & 0x80u) D3F_WIDE_RELOAD(3, code.w)
+            vec acc = LV::zero();
+            if (m & G::VIEWS) {
+                if ((m >> G::CHG) & G::VIEWS) {
+                    // reload the four corner texels of every view whose cell changed (32-bit element offsets: a view's
+                    // map spans fewer than 2^31 elements, checked on the host)
+                    int cv[NV];
+                    load_codes<NV>(a_code, p, cv);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        if (m & (1u << (G::CHG + v))) {
+                            const float* b_ = vbase[v] + (unsigned)(cv[v] & ~3);
+                            const unsigned dx_ = (cv[v] & 1) ? (unsigned)kp.sx : 0u;
+                            const unsigned dy_ = (cv[v] & 2) ? (unsigned)kp.sy : 0u;
+                            cc[v][0] = LV::ldg(b_); cc[v][1] = LV::ldg(b_ + dx_);
+                            cc[v][2] = LV::ldg(b_ + dy_); cc[v][3] = LV::ldg(b_ + (dy_ + dx_));
+                        }
+                    }
                 }
-#if D3F_WALK_FFMA2
-                // software-pipelined: the weight reads of view v+2 are issued behind the FMAs of view v, so two views'
-                // weights (16 registers) are in flight at a time
-                float4 wa0, wb0, wa1, wb1;
-                const float4* wp = sm.w4 + (size_t)p * (TILE_V * 2);
-                if (m & 1u) { wa0 = wp[0]; wb0 = wp[1]; }
-                if (m & 2u) { wa1 = wp[2]; wb1 = wp[3]; }
-                if (m & 1u) D3F_WIDE_FMA(0, wa0, wb0)
-                if (m & 4u) { wa0 = wp[4]; wb0 = wp[5]; }
-                if (m & 2u) D3F_WIDE_FMA(1, wa1, wb1)
-                if (m & 8u) { wa1 = wp[6]; wb1 = wp[7]; }
-                if (m & 4u) D3F_WIDE_FMA(2, wa0, wb0)
-                if (m & 8u) D3F_WIDE_FMA(3, wa1, wb1)
-                acc = make_float4(acc01.x, acc01.y, acc23.x, acc23.y);
-#else
-                // the weight reads of every visible view are issued before the first FMA.  (Dispatching on the four
-                // visibility bits with a 16-way switch instead of this if-chain compiles to a compare tree, not an
+                // the weight reads of every visible view are issued before the first FMA.  (Dispatching on the
+                // visibility bits with a switch instead of this if-chain compiles to a compare tree, not an
                 // indexed branch, and measured 3 % slower: profiles/r02_experiment_switch_dispatch.jsonl.)
-                float4 w0, w1, w2, w3;
-                const unsigned aw = a_w4 + p * (TILE_V * 16);
-                if (m & 1u) w0 = lds_f4(aw);
-                if (m & 2u) w1 = lds_f4(aw + 16);
-                if (m & 4u) w2 = lds_f4(aw + 32);
-                if (m & 8u) w3 = lds_f4(aw + 48);
-                if (m & 1u) D3F_WIDE_FMA1(0, w0)
-                if (m & 2u) D3F_WIDE_FMA1(1, w1)
-                if (m & 4u) D3F_WIDE_FMA1(2, w2)
-                if (m & 8u) D3F_WIDE_FMA1(3, w3)
-#endif
+                float4 w[NV];
+                const unsigned aw = a_w4 + p * (NV * 16);
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    if (m & (1u << v)) w[v] = lds_f4(aw + 16 * v);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    if (m & (1u << v)) {                                    // corner order nw, ne, sw, se; views in order
+                        LV::fma(acc, w[v].x, cc[v][0]); LV::fma(acc, w[v].y, cc[v][1]);
+                        LV::fma(acc, w[v].z, cc[v][2]); LV::fma(acc, w[v].w, cc[v][3]);
+                    }
+                }
             }
-            if (ORDERED) __stcs(reinterpret_cast<float4*>(o_col + (size_t)sm.row[p] * C), acc);
-            else         __stcs(reinterpret_cast<float4*>(o), acc);
+            if (ORDERED) LV::stcs(o_col + (size_t)sm.row[p] * C, acc);
+            else         LV::stcs(o, acc);
         }
     }
 }
 
-template <typename T, int VEC, bool ORDERED, bool WIDE>
-__device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<WIDE>& sm) {
+template <typename T, int VEC, bool ORDERED, bool WIDE, int NV>
+__device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<WIDE, NV>& sm) {
     const int C = kp.C;
     const int G = C / VEC;
     const T* __restrict__ vol = static_cast<const T*>(kp.data);
-    const int* codes = reinterpret_cast<const int*>(sm.code);
     for (int item = threadIdx.x; item < npts * G; item += TILE_THREADS) {
         const int p = item / G;
         const int c = (item - p * G) * VEC;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int v = 0; v < TILE_V; ++v) {
-            const int cv = codes[p * TILE_V + v];
+        for (int v = 0; v < NV; ++v) {
+            const int cv = sm.code[p * NV + v];
             if (cv < 0) continue;
             const T* b = vol + (size_t)v * (size_t)kp.sv + (size_t)(cv >> 2) + c;
             const int dx = (cv & 1) ? kp.sx : 0, dy = (cv & 2) ? kp.sy : 0;
-            const float4 w = sm.w4[p * TILE_V + v];
+            const float4 w = sm.w4[p * NV + v];
             if (VEC == 4) {
                 fma4(acc, w.x, Load4<T>::ld(b)); fma4(acc, w.y, Load4<T>::ld(b + dx));
                 fma4(acc, w.z, Load4<T>::ld(b + dy)); fma4(acc, w.w, Load4<T>::ld(b + dy + dx));
@@ -284,34 +282,31 @@ __device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t t
 __host__ __device__ inline long long key_extent(int h, int w, int C, long long sy, long long sx) {
     return (long long)(h - 1) * sy + (long long)(w - 1) * sx + C;
 }
-// wide-path eligibility of one key (host and device agree through this one function)
-__host__ __device__ inline bool key_is_wide(int dtype, int C, int h, int w, long long sv, long long sy, long long sx) {
-    return dtype == D3F_F32 && (C % 128) == 0 && ((sv | sy | sx) & 3) == 0 && key_extent(h, w, C, sy, sx) < (1ll << 31);
+// wide-path eligibility of one key for a slice of `slice` channels (host and device agree through this one function)
+__host__ __device__ inline bool key_is_wide(int dtype, int C, int h, int w, long long sv, long long sy, long long sx, int slice) {
+    return dtype == D3F_F32 && (C % slice) == 0 && ((sv | sy | sx) & 3) == 0 && key_extent(h, w, C, sy, sx) < (1ll << 31);
 }
 // the tile kernel's narrow path packs (offset << 2 | step bits) into 31 bits
-__host__ __device__ inline bool key_fits_tile(int dtype, int C, int h, int w, long long sv, long long sy, long long sx) {
-    return key_is_wide(dtype, C, h, w, sv, sy, sx) || key_extent(h, w, C, sy, sx) < (1ll << 29);
+__host__ __device__ inline bool key_fits_tile(int dtype, int C, int h, int w, long long sv, long long sy, long long sx, int slice) {
+    return key_is_wide(dtype, C, h, w, sv, sy, sx, slice) || key_extent(h, w, C, sy, sx) < (1ll << 29);
 }
 
 // WIDE=false compiles the register-cached walk out: launches with only narrow keys (instance masks, colours,
 // PCA-projected volumes) or no keys at all (dist / valid_mask sweeps) then need ~60 registers and run 4 CTAs
 // per SM instead of 2.
-template <bool RECIP, int VARIANT, bool WIDE, bool ORDERED>
+template <bool RECIP, int VARIANT, bool WIDE, bool ORDERED, int NV>
 __global__ void __launch_bounds__(TILE_THREADS, WIDE ? 2 : 4)
 field_tile_kernel(const EvalParams ep, const KeySet ks) {
-#if D3F_WALK_FFMA2
-    extern __shared__ __align__(16) unsigned char tile_smem_raw[];       // sizeof(TileSmemT<WIDE>), above 48 KB when WIDE
-    TileSmemT<WIDE>& sm = *reinterpret_cast<TileSmemT<WIDE>*>(tile_smem_raw);
-#else
-    __shared__ TileSmemT<WIDE> sm;
-#endif
+    using G = TileGeom<NV>;
+    constexpr int PTS = G::PTS;
+    __shared__ TileSmemT<WIDE, NV> sm;
     const int V = ep.V;
     const bool eval_dist = (ep.flags & D3F_FLAG_EVAL_DIST) != 0;
     // Tiles are taken in order.  Dealing them to the CTAs with a stride (so that the CTAs resident at one time mix
     // all-zero store-bound rows with issue-bound visible rows) was measured and is slower: 0.798 vs 0.781 ms on cfg2a,
     // 2.15 vs 1.92 ms on cfg2b (profiles/r02_experiment_tile_stride.jsonl) — neighbouring tiles share texels in L1/L2.
-    const int64_t tile0 = (int64_t)blockIdx.x * TILE_PTS;
-    const int npts = (int)min((int64_t)TILE_PTS, ep.n - tile0);
+    const int64_t tile0 = (int64_t)blockIdx.x * PTS;
+    const int npts = (int)min((int64_t)PTS, ep.n - tile0);
 
     for (int r = threadIdx.x; r < V * 3; r += TILE_THREADS) {
         const int v = r / 3, i = r - v * 3;
@@ -323,8 +318,8 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
     __syncthreads();
 
     // phase 1: view-major so a warp walks 32 consecutive points of one view
-    for (int item = threadIdx.x; item < TILE_PTS * V; item += TILE_THREADS) {
-        const int v = item / TILE_PTS, p = item - v * TILE_PTS;
+    for (int item = threadIdx.x; item < PTS * V; item += TILE_THREADS) {
+        const int v = item / PTS, p = item - v * PTS;
         if (p >= npts) continue;
         int64_t row = tile0 + p;
         if (ORDERED) {
@@ -337,7 +332,7 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
 #pragma unroll
         for (int j = 0; j < 12; ++j) Hm[j] = sm.H[v * 12 + j];
         ViewSample smp = view_sample<RECIP>(Hm, x, y, z, ep.depth + (size_t)v * ep.H * ep.W, ep.H, ep.W, ep.mu, eval_dist);
-        const int s = p * TILE_V + v;
+        const int s = p * NV + v;
         sm.px[s] = smp.px; sm.py[s] = smp.py;
         sm.d[s] = eval_dist ? smp.d : fminf(fmaxf(smp.d, -ep.mu), ep.mu);    // fusion.py:358
         sm.fac[s] = smp.weight;
@@ -350,14 +345,14 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
         const int p = threadIdx.x;
         float acc = 0.f, cnt = 0.f;
         for (int v = 0; v < V; ++v)
-            if (sm.vis[p * TILE_V + v]) { acc = __fadd_rn(acc, sm.d[p * TILE_V + v]); cnt = __fadd_rn(cnt, 1.f); }
+            if (sm.vis[p * NV + v]) { acc = __fadd_rn(acc, sm.d[p * NV + v]); cnt = __fadd_rn(cnt, 1.f); }
         const float denom = __fadd_rn(cnt, 1e-6f);
         float dist = __fdiv_rn(acc, denom);
         if (!eval_dist && cnt == 0.f) dist = 1e3f;                           // fusion.py:367
         store_compact(ep, ORDERED ? sm.row[p] : tile0 + p, dist, cnt != 0.f ? 1 : 0);
         const float inv = __fdiv_rn(1.f, denom);
         for (int v = 0; v < V; ++v) {
-            const int s = p * TILE_V + v;
+            const int s = p * NV + v;
             sm.fac[s] = sm.vis[s] ? __fmul_rn(sm.fac[s], inv) : 0.f;          // weight/(count+1e-6), fusion.py:385
         }
     }
@@ -367,70 +362,63 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
     }
     __syncthreads();
 
-    int* codes = reinterpret_cast<int*>(sm.code);
     for (int k = 0; k < ks.n_keys; ++k) {
         const KeyParams& kp = ks.k[k];
-        const bool wide = WIDE && key_is_wide(ks.dtype[k], kp.C, kp.h, kp.w, kp.sv, kp.sy, kp.sx);
-        for (int s = threadIdx.x; s < TILE_PTS * TILE_V; s += TILE_THREADS) {
-            const int p = s >> 2, v = s & 3;
+        const bool wide = WIDE && key_is_wide(ks.dtype[k], kp.C, kp.h, kp.w, kp.sv, kp.sy, kp.sx, G::SLICE);
+        for (int s = threadIdx.x; s < PTS * NV; s += TILE_THREADS) {
+            const int p = s >> G::LOG_NV, v = s & (NV - 1);
             int code = -1;
             if (p < npts && v < V && sm.vis[s]) {
                 const Footprint f = footprint<RECIP>(sm.px[s], sm.py[s], ep.H, ep.W, kp.h, kp.w);
                 const float fac = sm.fac[s];
-                const float w0 = f.w[0] * fac, w1 = f.w[1] * fac, w2 = f.w[2] * fac, w3 = f.w[3] * fac;
-                if (WIDE && WALK_FFMA2 && wide) {
-                    sm.w4[2 * s] = make_float4(w0, w0, w1, w1);
-                    sm.w4[2 * s + 1] = make_float4(w2, w2, w3, w3);
-                } else {
-                    sm.w4[s] = make_float4(w0, w1, w2, w3);
-                }
+                sm.w4[s] = make_float4(f.w[0] * fac, f.w[1] * fac, f.w[2] * fac, f.w[3] * fac);
                 const int eo = f.y0 * kp.sy + f.x0 * kp.sx;
                 code = (wide ? eo : (eo << 2)) | (f.dx ? 1 : 0) | (f.dy ? 2 : 0);
             }
-            codes[s] = code;
+            sm.code[s] = code;
         }
         __syncthreads();
         if (wide) {
             // per-point mask: which views see the point, and which of those changed texel cell since the
             // previous point of the same run (a view the previous point did not see always reloads)
-            if (threadIdx.x < TILE_PTS) {
+            if (threadIdx.x < PTS) {
                 const int p = threadIdx.x;
-                const int run = wide_run_len(kp.C >> 7);
-                const int4 c = sm.code[p];
+                const int run = wide_run_len(kp.C / G::SLICE, PTS);
                 const bool first = (p % run) == 0;
-                const int4 q = first ? make_int4(-1, -1, -1, -1) : sm.code[p - 1];
                 unsigned m = 0;
                 if (p < npts) {
-                    if (c.x >= 0) m |= 0x01u | ((c.x != q.x) ? 0x10u : 0u);
-                    if (c.y >= 0) m |= 0x02u | ((c.y != q.y) ? 0x20u : 0u);
-                    if (c.z >= 0) m |= 0x04u | ((c.z != q.z) ? 0x40u : 0u);
-                    if (c.w >= 0) m |= 0x08u | ((c.w != q.w) ? 0x80u : 0u);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const int c = sm.code[p * NV + v];
+                        const int q = first ? -1 : sm.code[(p - 1) * NV + v];
+                        if (c >= 0) m |= (1u << v) | ((c != q) ? (1u << (G::CHG + v)) : 0u);
+                    }
                 }
                 sm.mask[p] = (int)m;
             }
-            if (threadIdx.x < 4) sm.mask[TILE_PTS + threadIdx.x] = 0;     // padding read by the walk's lookahead
+            if (threadIdx.x < 4) sm.mask[PTS + threadIdx.x] = 0;         // padding read by the walk's lookahead
             if (VARIANT & 4) {
                 __syncthreads();
                 int ahead = 0;
-                if (threadIdx.x < TILE_PTS) {
+                if (threadIdx.x < PTS) {
                     const int p = threadIdx.x;
-                    const int run = wide_run_len(kp.C >> 7);
-                    if ((p % run) + WIDE_LOOKAHEAD < run && p + WIDE_LOOKAHEAD < TILE_PTS)
-                        ahead = (sm.mask[p + WIDE_LOOKAHEAD] & 0xF0) << 8;
+                    const int run = wide_run_len(kp.C / G::SLICE, PTS);
+                    if ((p % run) + WIDE_LOOKAHEAD < run && p + WIDE_LOOKAHEAD < PTS)
+                        ahead = ((sm.mask[p + WIDE_LOOKAHEAD] >> G::CHG) & G::VIEWS) << G::AHEAD;
                 }
                 __syncthreads();
-                if (threadIdx.x < TILE_PTS) sm.mask[threadIdx.x] |= ahead;
+                if (threadIdx.x < PTS) sm.mask[threadIdx.x] |= ahead;
             }
             __syncthreads();
-            if constexpr (WIDE) wide_accumulate<(VARIANT & 4) != 0, ORDERED>(kp, tile0, npts, sm);
+            if constexpr (WIDE) wide_accumulate<(VARIANT & 4) != 0, ORDERED, NV>(kp, tile0, npts, sm);
         } else {
             const bool vec4 = (kp.C % 4 == 0) && ((kp.sv | kp.sy | kp.sx) & 3) == 0;
             if (ks.dtype[k] == D3F_F32) {
-                if (vec4) narrow_accumulate<float, 4, ORDERED, WIDE>(kp, tile0, npts, sm);
-                else      narrow_accumulate<float, 1, ORDERED, WIDE>(kp, tile0, npts, sm);
+                if (vec4) narrow_accumulate<float, 4, ORDERED, WIDE, NV>(kp, tile0, npts, sm);
+                else      narrow_accumulate<float, 1, ORDERED, WIDE, NV>(kp, tile0, npts, sm);
             } else {
-                if (vec4) narrow_accumulate<uint8_t, 4, ORDERED, WIDE>(kp, tile0, npts, sm);
-                else      narrow_accumulate<uint8_t, 1, ORDERED, WIDE>(kp, tile0, npts, sm);
+                if (vec4) narrow_accumulate<uint8_t, 4, ORDERED, WIDE, NV>(kp, tile0, npts, sm);
+                else      narrow_accumulate<uint8_t, 1, ORDERED, WIDE, NV>(kp, tile0, npts, sm);
             }
         }
         __syncthreads();

@@ -63,6 +63,9 @@ ORACLE_CASES = [
     (6, 120, 160, (12, 16, 12), 5, (11, 13, 7), 1234, 14),
     (3, 97, 131, (97, 131, 7), 3, (10, 10, 10), 777, 15),            # full-resolution map, odd C
     (16, 48, 64, (5, 7, 3), 0, (8, 8, 8), 100, 16),                  # D3F_MAX_VIEWS
+    (5, 120, 160, (12, 16, 128), 4, (14, 14, 9), 1500, 17),          # 5-8 views: the NV = 8 tile instantiation
+    (8, 120, 160, (12, 16, 1024), 0, (12, 12, 12), 1500, 18),
+    (7, 97, 131, (10, 13, 64), 3, (10, 10, 10), 900, 19),            # one 64-channel slice: tile split into runs
 ]
 
 
@@ -89,6 +92,15 @@ def test_matches_oracle(case, mask_u8):
         none = ~ref['valid_mask']
         assert (got[k][none] == 0).all()
     assert (got['dist'][~ref['valid_mask']] == np.float32(1e3)).all()
+    # the same query without per-view outputs takes the tile kernel for V <= 8 (the generic kernel above that)
+    got2 = _np(f.eval(torch.from_numpy(pts).to(DEV), return_names=names))
+    want = 'generic' if V > 8 else ('tile/wide' if feat[2] % (128 if V <= 4 else 64) == 0 else 'tile/narrow')
+    assert _native.last_variant(0) == want, (_native.last_variant(0), want)
+    assert_bits_equal(got2['valid_mask'], ref['valid_mask'], 'valid_mask (tile)')
+    assert_bits_equal(got2['dist'], ref['dist'], 'dist (tile)')
+    for k in names:
+        assert_close_field(got2[k], ref[k], what=k + ' (tile)')
+        assert (got2[k][~ref['valid_mask']] == 0).all()
     gd = _np(f.eval_dist(torch.from_numpy(pts).to(DEV)))
     rd = O.field_eval(pts, sc.pose, sc.K, sc.depth, H, W, eval_dist=True)
     assert_bits_equal(gd['dist'], rd['dist'], 'eval_dist.dist')

@@ -197,6 +197,19 @@ def main():
         ms, mn = timed(lambda: f.eval(grid1m, ['dino_feats', 'mask', 'color_tensor']), flush=flush)
         rec('vis_repr_3keys', 1_000_000, ms, mn, [(48, 64, 1024, 4), (480, 640, 8, 4), (480, 640, 3, 4)],
             'dino_feats+mask+color_tensor in one launch (reference vis_repr.py:103)')
+    if want('v8'):
+        # eight views: the NV = 8 tile instantiation (64-channel slices); D3F_FORCE_GENERIC=1 in the environment gives the
+        # generic kernel's time for the same launch
+        sc8 = S.make_scene(8, H, W, seed=0, feat=(48, 64, 1024))
+        f8 = Fusion(num_cam=8, device=DEV)
+        f8.update({'depth': sc8.depth, 'pose': sc8.pose, 'K': sc8.K, 'dino_feats': sc8.maps['dino_feats']})
+        ms, mn = timed(lambda: f8.eval(grid1m, ['dino_feats']), flush=flush)
+        B8 = 12 * 1_000_000 + 8 * H * W * 4 + 8 * 48 * 64 * 1024 * 4 + 1_000_000 * (5 + 4096)
+        r = dict(name='v8_grid_1m', n=1_000_000, ms=ms, ms_min=mn, mpts_s=1_000_000 / ms / 1e3, alg_bytes=B8, gbs=B8 / ms / 1e6,
+                 frac_of_measured_hbm=B8 / ms / 1e6 / peak, variant=_native.last_variant(0), valid=float(f8.eval(grid1m, [])['valid_mask'].float().mean()),
+                 note='V=8 ring cameras, 1M grid points, C=1024 @ (48,64)')
+        results.append(r); print(json.dumps(r), flush=True)
+        del f8
     if want('cfg2b'):
         vol = f.curr_obs_torch['dino_feats']
         try:
