@@ -114,7 +114,16 @@ def _as_device(t, device, dtype=None):
 
 
 class Fusion:
-    """The per-frame multi-view field (reference fusion.py:202) with a CUDA-native query path."""
+    """The per-frame multi-view field (reference fusion.py:202) with a CUDA-native query path.
+
+    index_rounding — which of torch's two roundings of the pixel normalisation the integer decisions replay:
+      'cpu' (default)  x_n = p / (W-1) * 2 - 1, index = (x_n + 1) * ((size-1)/2): torch's CPU kernels.  This is the parity
+                       oracle: the unmodified reference was run on CPU to produce tests/golden/, and dist / valid_mask
+                       match it bit for bit.
+      'cuda'           x_n = p * (1/(W-1)) * 2 - 1, index = ((x_n + 1)/2) * (size-1): torch's CUDA kernels, i.e. what a
+                       user of the reference on its default device ('cuda:0', fusion.py:203) gets.  The two differ only
+                       for points within an ulp of a pixel/texel boundary (a few per million: nearest-depth pixel, bilinear
+                       cell, hence visibility); set it when comparing against a GPU run of the reference."""
 
     def __init__(self, num_cam, feat_backbone='dinov2', device='cuda:0', dtype=torch.float32,
                  feature_extractor: Optional[Callable] = None, perception=None):

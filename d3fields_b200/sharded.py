@@ -44,7 +44,11 @@ def bind_to_gpu_numa(device_index: int) -> str:
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        try:                                                # CUDA_VISIBLE_DEVICES may renumber: go through the UUID
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+        except Exception:                                   # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
         ncpu = os.cpu_count() or 1
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
