@@ -37,6 +37,16 @@ namespace d3f {
 constexpr int TILE_THREADS = 256;
 constexpr int TILE_MAX_V = 8;            // views the tile kernel handles (more: field_generic_kernel)
 
+// D3F_ZERO_RUN_TMA=1: rows no view sees are not stored by the walk; every aligned group of ZERO_RUN_ROWS such rows is
+// written by ONE bulk-copy (TMA) store, cp.async.bulk shared -> global, from a zeroed block of shared memory (the
+// px/py/d/fac arrays, dead once the last key's footprints exist).  Round 1 measured one 4 KB bulk store per zero row as
+// slower than LSU stores; this is the batched form.  Measured: profiles/r02_experiment_zero_run_tma.jsonl.
+#ifndef D3F_ZERO_RUN_TMA
+#define D3F_ZERO_RUN_TMA 0
+#endif
+constexpr int ZERO_RUN_ROWS = 4;         // rows per bulk store: 16 KB at C = 1024
+constexpr unsigned ZERO_SKIP_BIT = 1u << 31;
+
 // Geometry of a tile for NV view slots (4 or 8; a launch with V views uses the smallest NV >= V).
 template <int NV>
 struct TileGeom {
@@ -200,6 +210,9 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
                     }
                 }
             }
+#if D3F_ZERO_RUN_TMA
+            if (m & ZERO_SKIP_BIT) continue;                          // this row is part of a bulk-stored run of zero rows
+#endif
             vec acc = LV::zero();
             if (m & G::VIEWS) {
                 if ((m >> G::CHG) & G::VIEWS) {
@@ -410,7 +423,38 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
                 if (threadIdx.x < PTS) sm.mask[threadIdx.x] |= ahead;
             }
             __syncthreads();
+#if D3F_ZERO_RUN_TMA
+            // runs of rows no view sees -> bulk stores from a zeroed shared block (only when no later key needs px..fac)
+            bool issued_bulk = false;
+            if (!ORDERED && k == ks.n_keys - 1 && (size_t)ZERO_RUN_ROWS * kp.C * 4 <= sizeof(float) * 4 * PTS * NV) {
+                float4* zsrc = reinterpret_cast<float4*>(sm.px);                       // px, py, d, fac are contiguous
+                const int zn = ZERO_RUN_ROWS * kp.C / 4;
+                for (int i = threadIdx.x; i < zn; i += TILE_THREADS) zsrc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                const int p0 = threadIdx.x * ZERO_RUN_ROWS;
+                if (p0 + ZERO_RUN_ROWS <= npts) {
+                    bool all_zero = true;
+#pragma unroll
+                    for (int j = 0; j < ZERO_RUN_ROWS; ++j) all_zero = all_zero && ((sm.mask[p0 + j] & G::VIEWS) == 0);
+                    if (all_zero) {
+                        float* dst = kp.out + (size_t)(tile0 + p0) * kp.C;
+                        const unsigned src = (unsigned)__cvta_generic_to_shared(zsrc);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(dst), "r"(src), "r"((unsigned)(ZERO_RUN_ROWS * kp.C * 4)) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        issued_bulk = true;
+#pragma unroll
+                        for (int j = 0; j < ZERO_RUN_ROWS; ++j) sm.mask[p0 + j] |= (int)ZERO_SKIP_BIT;
+                    }
+                }
+                __syncthreads();
+            }
+#endif
             if constexpr (WIDE) wide_accumulate<(VARIANT & 4) != 0, ORDERED, NV>(kp, tile0, npts, sm);
+#if D3F_ZERO_RUN_TMA
+            if (issued_bulk) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the source block outlives its readers
+#endif
         } else {
             const bool vec4 = (kp.C % 4 == 0) && ((kp.sv | kp.sy | kp.sx) & 3) == 0;
             if (ks.dtype[k] == D3F_F32) {
