@@ -313,7 +313,7 @@ def tracking_latency(f, dev, iters=100):
     num_inst*100 points — as one CUDA-graph replay, against the same loop launched eagerly and against the reference
     operator sequence with torch autograd on the same GPU."""
     import torch
-    from d3fields_b200.tracking import RigidTracker
+    from d3fields_b200.tracking import FusedRigidTracker, RigidTracker
     from oracle import torch_port as TP
     I, P, C = 4, 100, CFG['feat'][2]
     pts = torch.from_numpy(S.scattered_points(I * P, 23, sigma=0.12)).to(dev).reshape(I, P, 3)
@@ -321,9 +321,9 @@ def tracking_latency(f, dev, iters=100):
     moved = pts + 0.004
     obs = {k: v for k, v in f.curr_obs_torch.items() if isinstance(v, torch.Tensor)}
     out = {}
-    for name, kw in (('graph', dict(graph=True)), ('eager', dict(graph=False)),
+    for name, kw in (('fused_graph', dict(fused=True)), ('graph', dict(graph=True)), ('eager', dict(graph=False)),
                      ('torch_reference_ops', dict(graph=False, eval_fn=lambda p, names: TP.eval_chunk(obs, f.H, f.W, p, names)))):
-        tr = RigidTracker(f, I, P, C, iters=iters, **kw)
+        tr = FusedRigidTracker(f, I, P, C, iters=iters) if kw.pop('fused', False) else RigidTracker(f, I, P, C, iters=iters, **kw)
         tr.track(src, moved)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
@@ -333,7 +333,9 @@ def tracking_latency(f, dev, iters=100):
         torch.cuda.synchronize(dev)
         out[name] = (time.perf_counter() - t0) / reps / iters * 1e6
     return {'points': I * P, 'iterations': iters, 'us_per_iteration': out,
-            'what': 'RigidTracker.track wall time / iterations: forward + backward + Adam step (reference fusion.py:1643-1665)'}
+            'what': 'track() wall time / iterations: forward + backward + Adam step (reference fusion.py:1643-1665). fused_graph: '
+                    '4 launches per iteration (d3f_eval, d3f_track_loss_grad, d3f_eval_backward, d3f_track_update) in one CUDA graph; '
+                    'graph / eager: torch autograd around the two field kernels; torch_reference_ops: the reference operator sequence'}
 
 
 def main():

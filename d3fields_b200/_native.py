@@ -23,7 +23,8 @@ D3F_ETIMEOUT = -4
 # every symbol include/d3f.h declares (tests check the built library exports exactly these)
 SYMBOLS = ('d3f_eval', 'd3f_eval_host', 'd3f_release_scratch', 'd3f_eval_ordered', 'd3f_bin_workspace_bytes',
            'd3f_bin_order', 'd3f_sweep_select', 'd3f_comm_create', 'd3f_comm_connect', 'd3f_comm_destroy',
-           'd3f_comm_status', 'd3f_eval_allgather', 'd3f_comm_broadcast', 'd3f_eval_backward', 'd3f_pca_project',
+           'd3f_comm_status', 'd3f_eval_allgather', 'd3f_comm_broadcast', 'd3f_eval_backward', 'd3f_track_loss_grad',
+           'd3f_track_update', 'd3f_pca_project',
            'd3f_create_grid', 'd3f_abi_version', 'd3f_last_error', 'd3f_launch_count', 'd3f_last_variant',
            'd3f_sizeof_key', 'd3f_sizeof_obs')
 
@@ -47,6 +48,15 @@ class D3FKey(C.Structure):
     _fields_ = [('data', C.c_void_p), ('dtype', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('C', C.c_int32),
                 ('stride_v', C.c_int64), ('stride_y', C.c_int64), ('stride_x', C.c_int64),
                 ('bias', C.c_void_p)]
+
+
+class D3FTrack(C.Structure):
+    _fields_ = [('t_in', C.c_void_p), ('r_in', C.c_void_p), ('t_out', C.c_void_p), ('r_out', C.c_void_p),
+                ('m_t', C.c_void_p), ('v_t', C.c_void_p), ('m_r', C.c_void_p), ('v_r', C.c_void_p),
+                ('last_pts', C.c_void_p), ('grad_pts', C.c_void_p), ('pts', C.c_void_p),
+                ('n_inst', C.c_int32), ('n_pts', C.c_int32),
+                ('step', C.c_float), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
+                ('reg_w', C.c_float)]
 
 
 class D3FGrid(C.Structure):
@@ -112,6 +122,10 @@ def load() -> C.CDLL:
     lib.d3f_eval_allgather.restype = C.c_int
     lib.d3f_comm_broadcast.argtypes = [vp, vp, i64, i32, vp]
     lib.d3f_comm_broadcast.restype = C.c_int
+    lib.d3f_track_loss_grad.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp, vp, vp, vp]
+    lib.d3f_track_loss_grad.restype = C.c_int
+    lib.d3f_track_update.argtypes = [C.POINTER(D3FTrack), vp]
+    lib.d3f_track_update.restype = C.c_int
     lib.d3f_sizeof_key.restype = C.c_int
     lib.d3f_sizeof_obs.restype = C.c_int
     lib.d3f_eval_backward.argtypes = [C.POINTER(D3FObs), vp, i64, C.POINTER(D3FKey), i32, C.POINTER(vp), vp, vp, u32, f32, vp]
@@ -261,6 +275,17 @@ def eval_backward(V: int, H: int, W: int, pose: int, K: int, depth: int, pts: in
     obs = D3FObs(V, H, W, pose, K, depth)
     _check(lib.d3f_eval_backward(C.byref(obs), pts, n, _keys_array(keys), len(keys), _ptr_array(grad_outs),
                                  grad_dist, grad_pts, flags, mu, stream))
+
+
+def track_loss_grad(feat: int, src: int, dist: int, valid: int, n: int, c: int, dist_w: float, g_feat: int, g_dist: int,
+                    loss_terms: Optional[int], stream: int) -> None:
+    _check(load().d3f_track_loss_grad(feat, src, dist, valid, n, c, dist_w, g_feat, g_dist, loss_terms, stream))
+
+
+def track_update(stream: int, **kw) -> None:
+    """d3f_track_update; keyword arguments are the fields of D3FTrack (device addresses / sizes / hyper-parameters)."""
+    t = D3FTrack(**kw)
+    _check(load().d3f_track_update(C.byref(t), stream))
 
 
 def pca_project(x: int, n: int, c: int, mean: int, comp: int, n_comp: int, y: int, stream: int) -> None:

@@ -116,8 +116,9 @@ void launch_tile(bool ordered, dim3 grid, dim3 block, cudaStream_t st, const d3f
     else         d3f::field_tile_kernel<RECIP, VARIANT, WIDE, false, NV><<<grid, block, 0, st>>>(ep, ks);
 }
 
-// NV = 4: up to four views (every configuration the reference runs).  NV = 8: five to eight views; the lookahead
-// prefetch variant is not instantiated there.
+// NV = 4: up to four views (every configuration the reference runs).  NV = 8: five to eight views.  NV = 0: four view
+// slots with 32-point tiles, for launches too small to fill the GPU with 256-point tiles (latency: a warp walks its
+// tile serially).  The lookahead prefetch variant is instantiated for NV = 4 only.
 template <int NV>
 void launch_tile_nv(bool recip, bool wide, bool prefetch, bool ordered, dim3 grid, dim3 block, cudaStream_t st,
                     const d3f::EvalParams& ep, const d3f::KeySet& ks) {
@@ -175,9 +176,12 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
         g_variant[k] = "generic";
     }
     // production path: point tiles, register-cached corner texels for wide float32 maps
-    const int nv = obs->V <= 4 ? 4 : 8;
-    const int slice = nv == 4 ? d3f::TileGeom<4>::SLICE : d3f::TileGeom<8>::SLICE;
-    const int tile_pts = nv == 4 ? d3f::TileGeom<4>::PTS : d3f::TileGeom<8>::PTS;
+    // small launches (tracking: a few hundred points; mesh vertices: tens of thousands) take 32-point tiles; measured
+    // crossover between 100 000 points (149 vs 171 us) and 150 000 (208 vs 182 us): profiles/r02_ab_small_tiles.jsonl
+    static const int64_t small_n = [] { const char* e = getenv("D3F_SMALL_TILE_N"); return e ? atoll(e) : 100000ll; }();
+    const int nv = obs->V <= 4 ? ((n <= small_n && !order) ? 0 : 4) : 8;
+    const int slice = nv == 8 ? d3f::TileGeom<8>::SLICE : d3f::TileGeom<4>::SLICE;
+    const int tile_pts = nv == 0 ? d3f::TileGeom<0>::PTS : (nv == 4 ? d3f::TileGeom<4>::PTS : d3f::TileGeom<8>::PTS);
     auto is_wide = [&](int k) {
         return d3f::key_is_wide(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w, ks.k[k].sv, ks.k[k].sy, ks.k[k].sx, slice);
     };
@@ -199,8 +203,9 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
         for (int k = 0; k < ks.n_keys; ++k)
             if (is_wide(k)) wide_bytes += (size_t)obs->V * keys[k].h * keys[k].w * keys[k].C * 4;
         const bool prefetch = force >= 0 ? force != 0 : wide_bytes > (size_t)(64u << 20);
-        if (nv == 4) launch_tile_nv<4>(recip, wide_bytes != 0, prefetch, order != nullptr, grid, block, st, ep, ks);
-        else         launch_tile_nv<8>(recip, wide_bytes != 0, prefetch, order != nullptr, grid, block, st, ep, ks);
+        if (nv == 4)      launch_tile_nv<4>(recip, wide_bytes != 0, prefetch, order != nullptr, grid, block, st, ep, ks);
+        else if (nv == 0) launch_tile_nv<0>(recip, wide_bytes != 0, false, false, grid, block, st, ep, ks);
+        else              launch_tile_nv<8>(recip, wide_bytes != 0, prefetch, order != nullptr, grid, block, st, ep, ks);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         D3F_CUDA(cudaGetLastError());
         return D3F_OK;
@@ -686,6 +691,44 @@ int d3f_eval_backward(const D3FObs* obs, const float* pts, int64_t n, const D3FK
         d3f::field_backward_kernel<true><<<(unsigned)blocks, d3f::BWD_WARPS * 32, 0, st>>>(ep, ks, grad_dist, grad_pts);
     else
         d3f::field_backward_kernel<false><<<(unsigned)blocks, d3f::BWD_WARPS * 32, 0, st>>>(ep, ks, grad_dist, grad_pts);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    D3F_CUDA(cudaGetLastError());
+    return D3F_OK;
+}
+
+int d3f_track_loss_grad(const float* feat, const float* src, const float* dist, const uint8_t* valid,
+                        int64_t n, int32_t C, float dist_w, float* g_feat, float* g_dist, float* loss_terms, void* stream) {
+    NvtxRange nvtx_("d3f_track_loss_grad");
+    if (n < 0 || n >= (1ll << 31) || C < 1) return fail(D3F_EINVAL, "track_loss_grad: n=%lld C=%d", (long long)n, C);
+    if (n > 0 && (!feat || !src || !dist || !valid || !g_feat || !g_dist)) return fail(D3F_EINVAL, "track_loss_grad: NULL pointer");
+    int rc = check_device();
+    if (rc) return rc;
+    if (n == 0) return D3F_OK;
+    const int warps = 8;
+    d3f::track_loss_grad_kernel<<<(unsigned)((n + warps - 1) / warps), warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        feat, src, dist, valid, (int)n, C, dist_w, g_feat, g_dist, loss_terms);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    D3F_CUDA(cudaGetLastError());
+    return D3F_OK;
+}
+
+int d3f_track_update(const D3FTrack* t, void* stream) {
+    NvtxRange nvtx_("d3f_track_update");
+    if (!t) return fail(D3F_EINVAL, "track_update: NULL");
+    if (t->n_inst < 0 || t->n_pts < 0) return fail(D3F_EINVAL, "track_update: negative sizes");
+    if (t->n_inst > 0 && (!t->t_in || !t->r_in || !t->last_pts)) return fail(D3F_EINVAL, "track_update: NULL pointer");
+    if (t->grad_pts && (!t->t_out || !t->r_out || !t->m_t || !t->v_t || !t->m_r || !t->v_r || t->t_out == t->t_in || t->r_out == t->r_in))
+        return fail(D3F_EINVAL, "track_update: an update needs moments and output buffers distinct from the inputs");
+    if (t->grad_pts && !(t->step >= 1.f)) return fail(D3F_EINVAL, "track_update: step=%g must be >= 1", (double)t->step);
+    int rc = check_device();
+    if (rc) return rc;
+    if (t->n_inst == 0) return D3F_OK;
+    d3f::TrackParams tp;
+    tp.t_in = t->t_in; tp.r_in = t->r_in; tp.t_out = t->t_out; tp.r_out = t->r_out;
+    tp.m_t = t->m_t; tp.v_t = t->v_t; tp.m_r = t->m_r; tp.v_r = t->v_r;
+    tp.last_pts = t->last_pts; tp.grad_pts = t->grad_pts; tp.pts = t->pts; tp.I = t->n_inst; tp.P = t->n_pts;
+    tp.step = t->step; tp.lr = t->lr; tp.beta1 = t->beta1; tp.beta2 = t->beta2; tp.eps = t->eps; tp.reg_w = t->reg_w;
+    d3f::track_update_kernel<<<(unsigned)t->n_inst, d3f::TRACK_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(tp);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     D3F_CUDA(cudaGetLastError());
     return D3F_OK;

@@ -72,4 +72,175 @@ create_grid_kernel(double x_lower, double y_lower, double z_lower, double step,
     pts[i * 3 + 2] = __fadd_rn((float)(z_lower + step * iz), half);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// rigid_tracking (reference fusion.py:1608-1685): the two small kernels that, together with the field query and its
+// backward, make one Adam iteration four launches (d3fields_b200/tracking.py, fused=True).
+//
+//   track_loss_grad_kernel   d loss / d feat and d loss / d dist of
+//                                loss = mean_p(|feat_p - src_p|_2 * valid_p) + dist_w * mean_p(max(dist_p * valid_p, 0)) + reg
+//                            (fusion.py:1651-1662); one warp per point.  torch's norm backward is diff/|diff| (0 at 0).
+//   track_update_kernel      per instance i: chain d loss / d pts (from d3f_eval_backward) through
+//                                pts = last_pts @ R(log_r) + t,  R = so3_exp_map(log_r)   (pytorch3d: I + sin(a)/a K + (1-cos a)/a^2 K^2,
+//                                a = sqrt(max(|log_r|^2, 1e-4)))
+//                            to t and log_r, add the gradient of reg_w * (|t|_F + |log_r|_F) (norms over ALL instances, 0 at 0),
+//                            take one Adam step (torch.optim.Adam defaults: betas, eps 1e-8, no weight decay, bias
+//                            correction as torch computes it) and write the NEXT iteration's points.
+constexpr int TRACK_THREADS = 128;
+
+__global__ void __launch_bounds__(256)
+track_loss_grad_kernel(const float* __restrict__ feat, const float* __restrict__ src, const float* __restrict__ dist,
+                       const uint8_t* __restrict__ valid, int n, int C, float dist_w,
+                       float* __restrict__ g_feat, float* __restrict__ g_dist, float* __restrict__ loss_terms) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n) return;
+    const float* f = feat + (size_t)p * C;
+    const float* s = src + (size_t)p * C;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = f[c] - s[c]; ss = fmaf(d, d, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = sqrtf(ss);
+    const float v = valid[p] ? 1.f : 0.f;
+    const float scale = (nrm > 0.f) ? v / (nrm * (float)n) : 0.f;
+    float* g = g_feat + (size_t)p * C;
+    for (int c = lane; c < C; c += 32) g[c] = (f[c] - s[c]) * scale;
+    if (lane == 0) {
+        const float dv = dist[p] * v;
+        g_dist[p] = (dv >= 0.f) ? dist_w * v / (float)n : 0.f;                // torch's clamp(min=0) passes the gradient where x >= 0
+        if (loss_terms) loss_terms[p] = (nrm * v + dist_w * fmaxf(dv, 0.f)) / (float)n;
+    }
+}
+
+struct TrackParams {
+    const float* t_in;        // (I,3) translation / axis-angle of this iteration ...
+    const float* r_in;
+    float* t_out;             // ... and of the next (ping-pong buffers: every block reads ALL instances' old parameters
+    float* r_out;             //     for the regulariser's norms, so new ones must not land in the same array)
+    float* m_t; float* v_t;   // Adam moments of t      (I,3), updated in place
+    float* m_r; float* v_r;   // Adam moments of log_r  (I,3)
+    const float* last_pts;    // (I,P,3)
+    const float* grad_pts;    // (I*P,3) d loss / d pts of this iteration, or nullptr: no update, only transform with *_in
+    float* pts;               // (I*P,3) out: points of the next iteration (nullptr: leave them, e.g. after the last step)
+    int I, P;
+    float step;               // Adam step number of this update (1, 2, ...)
+    float lr, beta1, beta2, eps, reg_w;
+};
+
+__device__ __forceinline__ void so3_exp(const float w[3], float R[9], float& a2_clamped, float& f1, float& f2) {
+    const float n2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    a2_clamped = fmaxf(n2, 1e-4f);
+    const float a = sqrtf(a2_clamped), inv = 1.f / a;
+    f1 = inv * sinf(a);
+    f2 = inv * inv * (1.f - cosf(a));
+    const float K[9] = {0.f, -w[2], w[1], w[2], 0.f, -w[0], -w[1], w[0], 0.f};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float kk = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) kk += K[i * 3 + k] * K[k * 3 + j];
+            R[i * 3 + j] = f1 * K[i * 3 + j] + f2 * kk + (i == j ? 1.f : 0.f);
+        }
+}
+
+__global__ void __launch_bounds__(TRACK_THREADS)
+track_update_kernel(const TrackParams tp) {
+    __shared__ float red[TRACK_THREADS / 32][12];
+    __shared__ float sR[9], sT[3];
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* last = tp.last_pts + (size_t)i * tp.P * 3;
+    if (tp.grad_pts) {
+        // g_t = sum_p g_p ;  M[a][b] = sum_p last_p[a] * g_p[b]   (d loss / d R for pts = last @ R)
+        float acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+        const float* g = tp.grad_pts + (size_t)i * tp.P * 3;
+        for (int p = tid; p < tp.P; p += TRACK_THREADS) {
+            const float gx = g[p * 3], gy = g[p * 3 + 1], gz = g[p * 3 + 2];
+            const float lx = last[p * 3], ly = last[p * 3 + 1], lz = last[p * 3 + 2];
+            acc[0] += gx; acc[1] += gy; acc[2] += gz;
+            acc[3] += lx * gx; acc[4] += lx * gy; acc[5] += lx * gz;
+            acc[6] += ly * gx; acc[7] += ly * gy; acc[8] += ly * gz;
+            acc[9] += lz * gx; acc[10] += lz * gy; acc[11] += lz * gz;
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            if (lane == 0) red[warp][k] = acc[k];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float G[12];
+            for (int k = 0; k < 12; ++k) { G[k] = 0.f; for (int w = 0; w < TRACK_THREADS / 32; ++w) G[k] += red[w][k]; }
+            const float* M = G + 3;
+            float w3[3] = {tp.r_in[i * 3], tp.r_in[i * 3 + 1], tp.r_in[i * 3 + 2]};
+            float t3[3] = {tp.t_in[i * 3], tp.t_in[i * 3 + 1], tp.t_in[i * 3 + 2]};
+            // regulariser: Frobenius norms over all instances (fusion.py:1654)
+            float nt = 0.f, nr = 0.f;
+            for (int k = 0; k < tp.I * 3; ++k) { nt += tp.t_in[k] * tp.t_in[k]; nr += tp.r_in[k] * tp.r_in[k]; }
+            nt = sqrtf(nt); nr = sqrtf(nr);
+            // d R / d w_j  (K = hat(w);  dK_j = hat(e_j))
+            float R[9], a2, f1, f2;
+            so3_exp(w3, R, a2, f1, f2);
+            const float n2 = w3[0] * w3[0] + w3[1] * w3[1] + w3[2] * w3[2];
+            const float a = sqrtf(a2);
+            float df1 = 0.f, df2 = 0.f;                         // d f / d a (zero while the angle is clamped)
+            if (n2 > 1e-4f) {
+                df1 = (a * cosf(a) - sinf(a)) / (a * a);
+                df2 = (a * sinf(a) - 2.f * (1.f - cosf(a))) / (a * a * a);
+            }
+            const float K[9] = {0.f, -w3[2], w3[1], w3[2], 0.f, -w3[0], -w3[1], w3[0], 0.f};
+            float KK[9];
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { float s = 0.f; for (int k = 0; k < 3; ++k) s += K[r * 3 + k] * K[k * 3 + c]; KK[r * 3 + c] = s; }
+            float g_w[3], g_t[3];
+            for (int j = 0; j < 3; ++j) {
+                float dK[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (j == 0) { dK[5] = -1.f; dK[7] = 1.f; } else if (j == 1) { dK[2] = 1.f; dK[6] = -1.f; } else { dK[1] = -1.f; dK[3] = 1.f; }
+                const float da = (n2 > 1e-4f) ? w3[j] / a : 0.f;
+                float s = 0.f;
+                for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+                    float dKK = 0.f;
+                    for (int k = 0; k < 3; ++k) dKK += dK[r * 3 + k] * K[k * 3 + c] + K[r * 3 + k] * dK[k * 3 + c];
+                    const float dR = f1 * dK[r * 3 + c] + f2 * dKK + df1 * da * K[r * 3 + c] + df2 * da * KK[r * 3 + c];
+                    s += M[r * 3 + c] * dR;
+                }
+                g_w[j] = s + (nr > 0.f ? tp.reg_w * w3[j] / nr : 0.f);
+                g_t[j] = G[j] + (nt > 0.f ? tp.reg_w * t3[j] / nt : 0.f);
+            }
+            // Adam (torch.optim.Adam, single-tensor path): step_size = lr / (1 - b1^k), denom = sqrt(v)/sqrt(1 - b2^k) + eps
+            const float bc1 = 1.f - powf(tp.beta1, tp.step), bc2s = sqrtf(1.f - powf(tp.beta2, tp.step));
+            const float step_size = tp.lr / bc1;
+            for (int j = 0; j < 3; ++j) {
+                float m = tp.m_t[i * 3 + j] = tp.beta1 * tp.m_t[i * 3 + j] + (1.f - tp.beta1) * g_t[j];
+                float v = tp.v_t[i * 3 + j] = tp.beta2 * tp.v_t[i * 3 + j] + (1.f - tp.beta2) * g_t[j] * g_t[j];
+                t3[j] -= step_size * m / (sqrtf(v) / bc2s + tp.eps);
+                m = tp.m_r[i * 3 + j] = tp.beta1 * tp.m_r[i * 3 + j] + (1.f - tp.beta1) * g_w[j];
+                v = tp.v_r[i * 3 + j] = tp.beta2 * tp.v_r[i * 3 + j] + (1.f - tp.beta2) * g_w[j] * g_w[j];
+                w3[j] -= step_size * m / (sqrtf(v) / bc2s + tp.eps);
+            }
+            for (int j = 0; j < 3; ++j) { tp.t_out[i * 3 + j] = t3[j]; tp.r_out[i * 3 + j] = w3[j]; sT[j] = t3[j]; }
+            float a2n, f1n, f2n;
+            so3_exp(w3, sR, a2n, f1n, f2n);
+        }
+    } else if (tid == 0) {
+        float w3[3] = {tp.r_in[i * 3], tp.r_in[i * 3 + 1], tp.r_in[i * 3 + 2]};
+        float a2, f1, f2;
+        so3_exp(w3, sR, a2, f1, f2);
+        sT[0] = tp.t_in[i * 3]; sT[1] = tp.t_in[i * 3 + 1]; sT[2] = tp.t_in[i * 3 + 2];
+    }
+    __syncthreads();
+    if (!tp.pts) return;
+    // pts = last @ R + t   (row vectors, pytorch3d Transform3d().rotate(R).translate(t))
+    for (int p = tid; p < tp.P; p += TRACK_THREADS) {
+        const float lx = last[p * 3], ly = last[p * 3 + 1], lz = last[p * 3 + 2];
+        float* o = tp.pts + ((size_t)i * tp.P + p) * 3;
+        o[0] = lx * sR[0] + ly * sR[3] + lz * sR[6] + sT[0];
+        o[1] = lx * sR[1] + ly * sR[4] + lz * sR[7] + sT[1];
+        o[2] = lx * sR[2] + ly * sR[5] + lz * sR[8] + sT[2];
+    }
+}
+
 }  // namespace d3f

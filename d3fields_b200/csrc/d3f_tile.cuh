@@ -48,10 +48,15 @@ constexpr int ZERO_RUN_ROWS = 4;         // rows per bulk store: 16 KB at C = 10
 constexpr unsigned ZERO_SKIP_BIT = 1u << 31;
 
 // Geometry of a tile for NV view slots (4 or 8; a launch with V views uses the smallest NV >= V).
-template <int NV>
+// NV = 0 is the latency geometry: 4 view slots and 32-point tiles.  A warp walks its tile's points one after the other,
+// so a launch of a few hundred points (rigid_tracking evaluates num_inst x 100, fusion.py:1650; select_features_* a few
+// hundred samples, fusion.py:1449) would put ~10 us of serial walk on two CTAs with 256-point tiles; 32-point tiles
+// spread it over 8x as many CTAs.
+template <int NVX>
 struct TileGeom {
-    static_assert(NV == 4 || NV == 8, "view slots per point: 4 or 8");
-    static constexpr int PTS = NV == 4 ? 256 : 128;      // 256-point tiles beat 128 by 4 % at NV = 4 (fewer barriers and cold starts)
+    static_assert(NVX == 0 || NVX == 4 || NVX == 8, "view slots per point: 4 or 8 (0: 4 slots, small tiles)");
+    static constexpr int NV = NVX == 0 ? 4 : NVX;
+    static constexpr int PTS = NVX == 0 ? 32 : (NV == 4 ? 256 : 128);   // 256-point tiles beat 128 by 4 % at NV = 4 (fewer barriers and cold starts)
     static constexpr int LOG_NV = NV == 4 ? 2 : 3;
     static constexpr int LANE_CH = NV == 4 ? 4 : 2;      // channels per lane: the register cache is NV x 4 corners x LANE_CH = 64
     static constexpr int SLICE = 32 * LANE_CH;           // channels a warp owns
@@ -61,9 +66,10 @@ struct TileGeom {
 };
 constexpr int TILE_PTS = TileGeom<4>::PTS;
 
-template <bool WIDE, int NV>
+template <bool WIDE, int NVX>
 struct TileSmemT {
-    static constexpr int PTS = TileGeom<NV>::PTS;
+    static constexpr int PTS = TileGeom<NVX>::PTS;
+    static constexpr int NV = TileGeom<NVX>::NV;
     float H[NV * 12];
     float px[PTS * NV];
     float py[PTS * NV];
@@ -155,9 +161,10 @@ constexpr int WIDE_LOOKAHEAD = 4;      // points between the L1 prefetch of a ce
 // PREFETCH: the lookahead bits of a point's mask word say which views change cell WIDE_LOOKAHEAD points later; the warp
 // then prefetches its own slice of those corner texels into L1, so the reload that follows is an L1 hit
 // instead of an L2 round trip with all eight warps of the CTA stalled on the same point.
-template <bool PREFETCH, bool ORDERED, int NV>
-__device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<true, NV>& sm) {
-    using G = TileGeom<NV>;
+template <bool PREFETCH, bool ORDERED, int NVX>
+__device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<true, NVX>& sm) {
+    using G = TileGeom<NVX>;
+    constexpr int NV = G::NV;
     using LV = LaneVec<G::LANE_CH>;
     using vec = typename LV::type;
     const int C = kp.C;
@@ -253,8 +260,9 @@ __device__ __forceinline__ void wide_accumulate(const KeyParams& kp, int64_t til
     }
 }
 
-template <typename T, int VEC, bool ORDERED, bool WIDE, int NV>
-__device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<WIDE, NV>& sm) {
+template <typename T, int VEC, bool ORDERED, bool WIDE, int NVX>
+__device__ __forceinline__ void narrow_accumulate(const KeyParams& kp, int64_t tile0, int npts, const TileSmemT<WIDE, NVX>& sm) {
+    constexpr int NV = TileGeom<NVX>::NV;
     const int C = kp.C;
     const int G = C / VEC;
     const T* __restrict__ vol = static_cast<const T*>(kp.data);
@@ -307,12 +315,13 @@ __host__ __device__ inline bool key_fits_tile(int dtype, int C, int h, int w, lo
 // WIDE=false compiles the register-cached walk out: launches with only narrow keys (instance masks, colours,
 // PCA-projected volumes) or no keys at all (dist / valid_mask sweeps) then need ~60 registers and run 4 CTAs
 // per SM instead of 2.
-template <bool RECIP, int VARIANT, bool WIDE, bool ORDERED, int NV>
+template <bool RECIP, int VARIANT, bool WIDE, bool ORDERED, int NVX>
 __global__ void __launch_bounds__(TILE_THREADS, WIDE ? 2 : 4)
 field_tile_kernel(const EvalParams ep, const KeySet ks) {
-    using G = TileGeom<NV>;
+    using G = TileGeom<NVX>;
     constexpr int PTS = G::PTS;
-    __shared__ TileSmemT<WIDE, NV> sm;
+    constexpr int NV = G::NV;
+    __shared__ TileSmemT<WIDE, NVX> sm;
     const int V = ep.V;
     const bool eval_dist = (ep.flags & D3F_FLAG_EVAL_DIST) != 0;
     // Tiles are taken in order.  Dealing them to the CTAs with a stride (so that the CTAs resident at one time mix
@@ -451,18 +460,18 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
                 __syncthreads();
             }
 #endif
-            if constexpr (WIDE) wide_accumulate<(VARIANT & 4) != 0, ORDERED, NV>(kp, tile0, npts, sm);
+            if constexpr (WIDE) wide_accumulate<(VARIANT & 4) != 0, ORDERED, NVX>(kp, tile0, npts, sm);
 #if D3F_ZERO_RUN_TMA
             if (issued_bulk) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the source block outlives its readers
 #endif
         } else {
             const bool vec4 = (kp.C % 4 == 0) && ((kp.sv | kp.sy | kp.sx) & 3) == 0;
             if (ks.dtype[k] == D3F_F32) {
-                if (vec4) narrow_accumulate<float, 4, ORDERED, WIDE, NV>(kp, tile0, npts, sm);
-                else      narrow_accumulate<float, 1, ORDERED, WIDE, NV>(kp, tile0, npts, sm);
+                if (vec4) narrow_accumulate<float, 4, ORDERED, WIDE, NVX>(kp, tile0, npts, sm);
+                else      narrow_accumulate<float, 1, ORDERED, WIDE, NVX>(kp, tile0, npts, sm);
             } else {
-                if (vec4) narrow_accumulate<uint8_t, 4, ORDERED, WIDE, NV>(kp, tile0, npts, sm);
-                else      narrow_accumulate<uint8_t, 1, ORDERED, WIDE, NV>(kp, tile0, npts, sm);
+                if (vec4) narrow_accumulate<uint8_t, 4, ORDERED, WIDE, NVX>(kp, tile0, npts, sm);
+                else      narrow_accumulate<uint8_t, 1, ORDERED, WIDE, NVX>(kp, tile0, npts, sm);
             }
         }
         __syncthreads();

@@ -138,3 +138,95 @@ class RigidTracker:
                     self._iteration()
         return {'match_pts': self.curr_pts.reshape(self.I, self.P, 3), 't': self.t.detach(), 'log_r': self.log_r.detach(),
                 'loss': self.loss}
+
+
+class FusedRigidTracker:
+    """RigidTracker with every torch op of the iteration replaced by two small kernels (d3f_track_loss_grad,
+    d3f_track_update): one Adam iteration = field query + loss gradient + field backward + pose update = four launches,
+    and the whole `iters`-iteration loop is one CUDA graph.  Same loop, loss, pose parametrisation and Adam arithmetic as
+    RigidTracker / the reference (fusion.py:1633-1665); agreement with the torch-autograd version is checked in
+    tests/test_tracking.py.  The observation (pose, K, depth, the descriptor map) is captured by address: update the
+    tensors of fusion.curr_obs_torch in place between frames, or call invalidate()."""
+
+    def __init__(self, fusion, num_instance: int, rand_ptcl_num: int, feat_dim: int, iters: int = 100, lr: float = 0.01,
+                 reg_w: float = 1.0, dist_w: float = 100.0, graph: bool = True, name: str = 'dino_feats'):
+        from . import _native
+        self._n = _native
+        self.fusion, self.iters, self.lr, self.reg_w, self.dist_w, self.name = fusion, iters, lr, reg_w, dist_w, name
+        self.use_graph = graph
+        dev = torch.device(fusion.device)
+        self.dev = dev
+        self.I, self.P, self.C = num_instance, rand_ptcl_num, feat_dim
+        n = num_instance * rand_ptcl_num
+        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+        self.t = [z(num_instance, 3), z(num_instance, 3)]          # ping-pong parameter buffers
+        self.r = [z(num_instance, 3), z(num_instance, 3)]
+        self.m_t, self.v_t, self.m_r, self.v_r = (z(num_instance, 3) for _ in range(4))
+        self.last_pts = z(num_instance, rand_ptcl_num, 3)
+        self.src_feats = z(n, feat_dim)
+        self.pts, self.grad_pts = z(n, 3), z(n, 3)
+        self.feat, self.g_feat = z(n, feat_dim), z(n, feat_dim)
+        self.dist, self.g_dist, self.loss_terms = z(n), z(n), z(n)
+        self.valid = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def invalidate(self):
+        self._graph = None
+
+    def _enqueue(self):
+        """The whole loop on torch's current stream: 1 + 4 * iters launches."""
+        N, f = self._n, self.fusion
+        V, H, W, pose_p, K_p, depth_p = f._obs_ptrs()
+        kt, _vol = f._key_tuple(self.name, V)
+        n = self.I * self.P
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        flags, mu = f._flags(False), float(f.mu)
+        common = dict(m_t=self.m_t.data_ptr(), v_t=self.v_t.data_ptr(), m_r=self.m_r.data_ptr(), v_r=self.v_r.data_ptr(),
+                      last_pts=self.last_pts.data_ptr(), n_inst=self.I, n_pts=self.P, lr=self.lr, beta1=0.9, beta2=0.999,
+                      eps=1e-8, reg_w=self.reg_w)
+        N.track_update(st, t_in=self.t[0].data_ptr(), r_in=self.r[0].data_ptr(), t_out=None, r_out=None, grad_pts=None,
+                       pts=self.pts.data_ptr(), step=0.0, **common)
+        for k in range(1, self.iters + 1):
+            a, b = (k - 1) % 2, k % 2
+            N.eval_device(V, H, W, pose_p, K_p, depth_p, self.pts.data_ptr(), n, [kt], self.dist.data_ptr(),
+                          self.valid.data_ptr(), [self.feat.data_ptr()], None, flags, mu, st)
+            N.track_loss_grad(self.feat.data_ptr(), self.src_feats.data_ptr(), self.dist.data_ptr(), self.valid.data_ptr(),
+                              n, self.C, self.dist_w, self.g_feat.data_ptr(), self.g_dist.data_ptr(),
+                              self.loss_terms.data_ptr(), st)
+            N.eval_backward(V, H, W, pose_p, K_p, depth_p, self.pts.data_ptr(), n, [kt], [self.g_feat.data_ptr()],
+                            self.g_dist.data_ptr(), self.grad_pts.data_ptr(), flags, mu, st)
+            N.track_update(st, t_in=self.t[a].data_ptr(), r_in=self.r[a].data_ptr(), t_out=self.t[b].data_ptr(),
+                           r_out=self.r[b].data_ptr(), grad_pts=self.grad_pts.data_ptr(),
+                           pts=self.pts.data_ptr() if k < self.iters else None,     # keep the last forward's points
+                           step=float(k), **common)
+
+    def _reset(self):
+        for x in (self.t[0], self.r[0], self.m_t, self.v_t, self.m_r, self.v_r):
+            x.zero_()
+
+    def track(self, src_feats: torch.Tensor, last_match_pts: torch.Tensor) -> Dict[str, torch.Tensor]:
+        with torch.cuda.device(self.dev):
+            self.src_feats.copy_(src_feats.reshape(self.src_feats.shape))
+            self.last_pts.copy_(last_match_pts.reshape(self.last_pts.shape))
+            self._reset()
+            if self.use_graph:
+                if self._graph is None:
+                    s = torch.cuda.Stream(self.dev)                     # warm-up outside the capture
+                    s.wait_stream(torch.cuda.current_stream(self.dev))
+                    with torch.cuda.stream(s):
+                        self._enqueue()
+                    torch.cuda.current_stream(self.dev).wait_stream(s)
+                    self._reset()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._enqueue()
+                    self._graph = g
+                self._graph.replay()
+            else:
+                self._enqueue()
+            fin = self.iters % 2
+            prev = (self.iters - 1) % 2                                  # parameters the last forward was computed with
+            data = self.loss_terms.sum()
+            loss = data + self.reg_w * (torch.norm(self.t[prev]) + torch.norm(self.r[prev]))
+        return {'match_pts': self.pts.reshape(self.I, self.P, 3), 't': self.t[fin], 'log_r': self.r[fin], 'loss': loss,
+                'data_loss': data}

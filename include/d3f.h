@@ -155,6 +155,33 @@ int d3f_eval_backward(const D3FObs* obs, const float* pts, int64_t n,
                       const float* const* grad_out, const float* grad_dist,
                       float* grad_pts, uint32_t flags, float mu, void* stream);
 
+/* rigid_tracking (reference fusion.py:1608-1685): with d3f_eval and d3f_eval_backward these two calls make one Adam
+ * iteration of the reference's loop four launches (d3fields_b200/tracking.py FusedRigidTracker captures 100 of them in
+ * one CUDA graph).
+ *
+ * d3f_track_loss_grad: gradients of  loss = mean_p(|feat_p - src_p|_2 * valid_p) + dist_w * mean_p(max(dist_p*valid_p, 0))
+ * (fusion.py:1651-1653) with respect to feat (n,C) and dist (n); loss_terms (n, nullable) receives each point's share. */
+int d3f_track_loss_grad(const float* feat, const float* src, const float* dist, const uint8_t* valid,
+                        int64_t n, int32_t C, float dist_w,
+                        float* g_feat, float* g_dist, float* loss_terms, void* stream);
+
+/* d3f_track_update: per instance, chain grad_pts (n_inst*n_pts,3; from d3f_eval_backward) through
+ * pts = last_pts @ so3_exp_map(log_r) + t  (pytorch3d conventions, fusion.py:1646-1648) to t and log_r, add the gradient
+ * of reg_w * (|t| + |log_r|) (Frobenius norms over all instances, fusion.py:1654), take Adam step number `step`
+ * (torch.optim.Adam defaults) from (t_in, r_in) into (t_out, r_out) — distinct buffers — and write the next iteration's
+ * points to pts.  grad_pts == NULL: no update, pts = transform with (t_in, r_in).  pts == NULL: no transform. */
+typedef struct D3FTrack {
+    const float* t_in;  const float* r_in;      /* (n_inst,3) */
+    float* t_out;       float* r_out;           /* (n_inst,3) */
+    float* m_t; float* v_t; float* m_r; float* v_r;   /* Adam moments (n_inst,3), updated in place */
+    const float* last_pts;                      /* (n_inst,n_pts,3) */
+    const float* grad_pts;                      /* (n_inst*n_pts,3) or NULL */
+    float* pts;                                 /* (n_inst*n_pts,3) or NULL */
+    int32_t n_inst, n_pts;
+    float step, lr, beta1, beta2, eps, reg_w;
+} D3FTrack;
+int d3f_track_update(const D3FTrack* tp, void* stream);
+
 /* Fused PCA projection of a descriptor field: y = (x - mean) @ components^T, the
  * sklearn.decomposition.PCA.transform the reference applies on the host to eval's
  * 'dino_feats' (reference fusion.py:1386-1392, weights from pca_model/*.pkl).

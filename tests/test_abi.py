@@ -71,9 +71,9 @@ def test_kernel_resource_contract():
         log = open(os.path.join(build.LIB_DIR, 'build.log')).read()
     blocks = re.findall(r"Function properties for (\S*field_tile_kernel\S*)\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, "
                         r"(\d+) bytes spill loads\nptxas info\s*: Used (\d+) registers", log)
-    assert len(blocks) >= 20, 'expected twenty instantiations of field_tile_kernel in the ptxas log'
+    assert len(blocks) >= 28, 'expected 28 instantiations of field_tile_kernel in the ptxas log'
     for name, stack, st, ld, regs in blocks:
-        wide = re.search(r'field_tile_kernelILb[01]ELi\d+ELb1ELb[01]ELi[48]EEE', name) is not None
+        wide = re.search(r'field_tile_kernelILb[01]ELi\d+ELb1ELb[01]ELi[048]EEE', name) is not None
         assert int(st) == 0 and int(ld) == 0, f'{name}: spills'
         assert int(regs) <= (128 if wide else 64), f'{name}: {regs} registers'
     sass = subprocess.run(['cuobjdump', '-sass', build.LIB_PATH], capture_output=True, text=True).stdout

@@ -95,3 +95,48 @@ def test_tracker_graph_replay_equals_eager_and_recovers_pose():
     ref_hp = RigidTracker(f, I, P, 256, iters=100, graph=True)
     r = ref_hp.track(src, moved)
     assert torch.isfinite(r['match_pts']).all() and torch.isfinite(r['loss'])
+
+
+@pytest.mark.gpu
+def test_fused_tracker_follows_the_torch_autograd_loop():
+    """FusedRigidTracker (four launches per Adam iteration, analytic pose gradient) against RigidTracker (torch autograd
+    around the same two field kernels): same trajectory with the reference's hyper-parameters (lr 0.01, reg_w 1,
+    dist_w 100) and with the gentle ones, rotation included; graph replay == eager launches; frame after frame."""
+    from d3fields_b200.tracking import FusedRigidTracker
+    from util import make_fusion
+    DEV = 'cuda:0'
+    sc = _trackable_scene(4, 240, 320, 24, 32, 256)
+    f = make_fusion(sc, DEV)
+    I, P = 3, 100
+    pts = torch.from_numpy(_surface_points(I, P, 5)).to(DEV)
+    src = f.eval(pts.reshape(-1, 3), return_names=['dino_feats'])['dino_feats']
+    shift = torch.tensor([[0.010, -0.006, 0.004], [-0.008, 0.005, 0.003], [0.004, 0.009, -0.004]], device=DEV)
+    # a small rotation about each set's centroid on top of the shift
+    w = torch.tensor([[0.02, -0.01, 0.015], [-0.015, 0.02, 0.01], [0.01, 0.01, -0.02]], device=DEV)
+    R = so3_exp_map(w)
+    c = pts.mean(dim=1, keepdim=True)
+    moved = torch.bmm(pts - c, R) + c - shift[:, None, :]
+    for kw in (dict(lr=0.001, reg_w=0.0), dict(lr=0.01, reg_w=1.0), dict(lr=0.003, reg_w=0.1, dist_w=10.0)):
+        ref = RigidTracker(f, I, P, 256, iters=60, graph=False, **kw).track(src, moved)
+        fe = FusedRigidTracker(f, I, P, 256, iters=60, graph=False, **kw)
+        fg = FusedRigidTracker(f, I, P, 256, iters=60, graph=True, **kw)
+        a, b = fe.track(src, moved), fg.track(src, moved)
+        assert torch.equal(a['t'], b['t']) and torch.equal(a['log_r'], b['log_r']) and torch.equal(a['match_pts'], b['match_pts'])
+        # Adam moves every parameter by ~lr per step whatever the gradient's scale, so near the optimum two float32
+        # implementations of the same gradient jitter apart by a fraction of lr: the bar is relative to the step and to lr
+        step = max(float((ref['t']).abs().max()), 1e-3)
+        assert (b['t'] - ref['t']).abs().max() <= 0.02 * step + 0.2 * kw['lr'], (kw, b['t'], ref['t'])
+        assert (b['log_r'] - ref['log_r']).abs().max() <= 0.02 * max(float(ref['log_r'].abs().max()), 1e-3) + 0.2 * kw['lr'], (kw, b['log_r'], ref['log_r'])
+        assert (b['match_pts'] - ref['match_pts']).abs().max() <= 3e-4 + 0.3 * kw['lr']
+        # the reported loss is the reference's (fusion.py:1651-1653) at the last forward's points.  (It cannot be compared
+        # with the other tracker's value tightly: |feat - src| over 256 channels changes by ~150 per metre, so 3e-4 m of
+        # trajectory jitter is 0.05 of loss.)
+        o = f.eval(b['match_pts'].reshape(-1, 3), return_names=['dino_feats'])
+        want = tracking_loss(o, src, torch.zeros(1, 3, device=DEV), torch.zeros(1, 3, device=DEV), reg_w=0.0,
+                             dist_w=kw.get('dist_w', 100.0))
+        assert abs(float(b['data_loss']) - float(want)) <= 1e-4 * abs(float(want)) + 1e-6
+        assert abs(float(b['loss']) - float(ref['loss'])) <= 0.25 * abs(float(ref['loss']))
+        print(kw, 'max |dt|', float((b['t'] - ref['t']).abs().max()), 'of', step, ' max |dlog_r|', float((b['log_r'] - ref['log_r']).abs().max()),
+              ' loss', float(b['loss']), float(ref['loss']))
+        c2 = fg.track(src, moved)                          # second frame: same graph, restarted state
+        assert torch.equal(c2['t'], b['t'])
