@@ -147,12 +147,14 @@ __device__ __forceinline__ float hdot(const float r[4], float x, float y, float 
 //   D3F_FLAG_RECIP_NORM:     ((p * (1/(img-1))) * 2 - 1 + 1) / 2 * (map-1)     (torch CUDA kernels)
 template <bool RECIP>
 __device__ __forceinline__ float to_map_index(float p, int img_size, int map_size) {
+    // the two halvings are multiplications by 0.5f: exact, like the division by 2 they stand for, without its ~10
+    // instructions (a quarter of the divisions of a point-view; the sweep and dist-only kernels are issue-bound on them)
     float n;
     if (RECIP) n = __fmul_rn(p, __fdiv_rn(1.f, (float)(img_size - 1)));
     else       n = __fdiv_rn(p, (float)(img_size - 1));
     n = __fsub_rn(__fmul_rn(n, 2.f), 1.f);
-    if (RECIP) return __fmul_rn(__fdiv_rn(__fadd_rn(n, 1.f), 2.f), (float)(map_size - 1));
-    return __fmul_rn(__fadd_rn(n, 1.f), __fdiv_rn((float)(map_size - 1), 2.f));
+    if (RECIP) return __fmul_rn(__fmul_rn(__fadd_rn(n, 1.f), 0.5f), (float)(map_size - 1));
+    return __fmul_rn(__fadd_rn(n, 1.f), __fmul_rn((float)(map_size - 1), 0.5f));
 }
 
 // One view of one point: everything Fusion.eval derives before it touches a feature map

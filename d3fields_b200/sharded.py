@@ -114,7 +114,7 @@ class PeerComm:
     are all-gathered through the group, and every rank maps its peers' segments.  torch.distributed is used for
     this handshake only; the data path afterwards is the field kernel's own remote stores and flags."""
 
-    def __init__(self, capacity_points: int, group=None, device=None, staging_bytes: int = 64 << 20):
+    def __init__(self, capacity_points: int, group=None, device=None, staging_bytes: int = 64 << 20, _connect: bool = True):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.group = group
@@ -122,14 +122,27 @@ class PeerComm:
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self._views: Dict[Tuple[int, str], torch.Tensor] = {}
         self._comm = None
+        self._handle = b''
         with torch.cuda.device(self.device):
-            self._comm, handle = _native.comm_create(self.rank, self.world, self.capacity, int(staging_bytes))
+            self._comm, self._handle = _native.comm_create(self.rank, self.world, self.capacity, int(staging_bytes))
+        if _connect:
+            self.connect(self.exchange_handles())
             if self.world > 1:
-                mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
-                allh = torch.empty(self.world * _native.D3F_IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
-                dist.all_gather_into_tensor(allh, mine, group=group)
-                _native.comm_connect(self._comm, bytes(allh.cpu().tolist()))
                 dist.barrier(group)
+
+    def exchange_handles(self, handle: Optional[bytes] = None) -> bytes:
+        """All-gather of the 64-byte IPC handles, rank order (collective)."""
+        if self.world == 1:
+            return b''
+        mine = torch.tensor(list(handle if handle is not None else self._handle), dtype=torch.uint8, device=self.device)
+        allh = torch.empty(self.world * _native.D3F_IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        return bytes(allh.cpu().tolist())
+
+    def connect(self, handles: bytes) -> None:
+        if self.world > 1:
+            with torch.cuda.device(self.device):
+                _native.comm_connect(self._comm, handles)
 
     def _view(self, ptr: int, kind: str) -> torch.Tensor:
         t = self._views.get((ptr, kind))
@@ -173,23 +186,44 @@ class PeerComm:
 
 
 def make_peer_comm(capacity_points: int, group=None, device=None, staging_bytes: int = 64 << 20) -> Optional[PeerComm]:
-    """PeerComm if every rank of the group could map its peers, else None on every rank (callers then use NCCL)."""
-    comm, ok = None, 1
-    try:
-        comm = PeerComm(capacity_points, group=group, device=device, staging_bytes=staging_bytes)
-    except (_native.D3FError, _native.NativeLibraryError, RuntimeError) as e:   # e.g. no peer access between two GPUs
-        import warnings
-        warnings.warn(f'peer-memory communicator unavailable on this rank: {e}', RuntimeWarning)
-        ok = 0
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dev = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
-        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    """PeerComm if every rank of the group could allocate its segment and map its peers', else None on EVERY rank
+    (callers then use the NCCL transport).  A failure on one rank never leaves the others waiting in a collective: the
+    ranks agree after each stage (create, map) with an all-reduce."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+
+    def agree(ok: bool) -> bool:
+        if world == 1:
+            return ok
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        ok = int(flag.item())
-    if not ok:
+        return bool(flag.item())
+
+    def warn(stage, e):
+        import warnings
+        warnings.warn(f'peer-memory communicator unavailable on this rank ({stage}): {e}', RuntimeWarning)
+
+    comm = None
+    try:
+        comm = PeerComm(capacity_points, group=group, device=device, staging_bytes=staging_bytes, _connect=False)
+    except (_native.D3FError, _native.NativeLibraryError, RuntimeError) as e:
+        warn('segment allocation', e)
+    if not agree(comm is not None):
         if comm is not None:
             comm.close()
         return None
+    handles = comm.exchange_handles()
+    ok = True
+    try:
+        comm.connect(handles)
+    except (_native.D3FError, RuntimeError) as e:          # e.g. no peer access between two of the GPUs
+        warn('mapping the peers', e)
+        ok = False
+    if not agree(ok):
+        comm.close()
+        return None
+    if world > 1:
+        dist.barrier(group)
     return comm
 
 
