@@ -380,6 +380,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback for the field query)')
+    local %= max(torch.cuda.device_count(), 1)      # a launcher that exposes one device per process
     # before any pinned allocation: this rank's threads and host buffers live next to its GPU
     numa = SH.bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
