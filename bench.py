@@ -545,10 +545,29 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         same = bool(torch.equal(host_out['dino_feats'][::997], out['dino_feats'][:ne][::997].cpu()))
+        # the ceiling this number sits under: plain pinned D2H copies of the same buffer, all ranks at once
+        d_probe = out['dino_feats'][:min(ne, 262144)]
+        h_probe = host_out['dino_feats'][:d_probe.shape[0]]
+        h_probe.copy_(d_probe, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        tp0 = time.perf_counter()
+        for _ in range(4):
+            h_probe.copy_(d_probe, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        tp = time.perf_counter() - tp0
+        if world > 1:
+            t = torch.tensor([tp], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tp = float(t.item())
+        link_gbs = 4 * d_probe.numel() * 4 / tp / 1e9
         e2e = {'value': world * ne * args.e2e_steps / dt / 1e6, 'unit': UNIT, 'points_per_gpu': ne,
                'h2d_bytes_per_step': int(world * ne * 12), 'd2h_bytes_per_step': int(world * ne * (5 + 4 * C)),
                'steps': args.e2e_steps, 'ms_per_step': dt / args.e2e_steps * 1e3, 'matches_device_path': same,
                'host_binding': numa,
+               'd2h_link_gbs_per_gpu_all_ranks_copying': link_gbs,
+               'link_ceiling_mpts_s': world * link_gbs * 1e9 / (5 + 4 * C) / 1e6,
                'api': 'Fusion.eval_host -> d3f_eval_host (pinned host buffers, slab-pipelined copies)'}
         del host_out
         if world == 1 and not args.no_extras:

@@ -107,7 +107,7 @@ int validate(const D3FObs* obs, const void* pts, int64_t n, const D3FKey* keys, 
     return D3F_OK;
 }
 
-// Device-pointer evaluation shared by d3f_eval and the slabs of d3f_eval_host.
+// a rank with no points still has to take part in the epoch exchange of a gathering launch
 __global__ void gather_only_kernel(const d3f::EvalParams ep) { d3f::gather_epilogue(ep); }
 
 template <bool RECIP, int VARIANT, bool WIDE, int NV>
@@ -134,6 +134,7 @@ void launch_tile_nv(bool recip, bool wide, bool prefetch, bool ordered, dim3 gri
     }
 }
 
+// Device-pointer evaluation shared by d3f_eval, d3f_eval_ordered, d3f_eval_allgather and the slabs of d3f_eval_host.
 int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* keys, int32_t n_keys,
                 float* dist, uint8_t* valid, float* const* out, float* const* out_inter,
                 uint32_t flags, float mu, cudaStream_t st,
