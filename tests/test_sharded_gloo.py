@@ -105,3 +105,37 @@ def test_block_interleaved_shares_and_deinterleave():
     assert torch.equal(deinterleave(torch.cat([f2[i] for i in idx]), world, block), f2)
     with pytest.raises(ValueError):
         block_interleaved_index(n + 1, 0, world, block)
+
+
+def test_share_plan_gather_index_formula_is_the_canonical_index():
+    """The in-kernel gather places local point i at base + (i // block) * stride + i % block (include/d3f.h,
+    d3f_eval_allgather).  For both layouts plan_share produces, that is the point's position in the full array."""
+    from d3fields_b200.sharded import Share, plan_share
+    import torch.distributed as dist
+    assert not dist.is_initialized()
+    pts = torch.arange(3 * 2 * 5 * 4 * 3, dtype=torch.float32).reshape(-1, 3)
+    n = pts.shape[0]
+    # world 1 through plan_share itself
+    for block in (None, 5):
+        sh = plan_share(pts, block=block)
+        i = torch.arange(sh.local.shape[0])
+        gi = sh.base + (i // sh.block) * sh.stride + i % sh.block
+        assert torch.equal(pts[gi], sh.local) and sh.n == n
+    # any world: the same formula with the ranks' parameters
+    for world in (2, 3, 4):
+        seen = torch.zeros(n, dtype=torch.int32)
+        for rank in range(world):
+            # contiguous slab
+            s, e = shard_range(n, rank, world)
+            i = torch.arange(e - s)
+            base, blk, stride = s, max(e - s, 1), 0
+            assert torch.equal(base + (i // blk) * stride + i % blk, torch.arange(s, e))
+        block = 5
+        if n % (block * world) == 0:
+            for rank in range(world):
+                idx = block_interleaved_index(n, rank, world, block)
+                i = torch.arange(idx.numel())
+                gi = rank * block + (i // block) * (world * block) + i % block
+                assert torch.equal(gi, idx)
+                seen[gi] += 1
+            assert (seen == 1).all()
