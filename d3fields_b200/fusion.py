@@ -12,6 +12,8 @@ Mirrors, for the hot path only, what reference fusion.py exposes and its drivers
   Fusion.batch_eval(pts, return_names)                 reference fusion.py:526-545
   Fusion.text_queries_for_inst_mask(_no_track)(...)    reference fusion.py:1173 / :1112 (delegated, see below)
   Fusion.get_inst_num()                                reference fusion.py:1258
+  Fusion.select_features_rand / _from_pcd(...)         reference fusion.py:1418 / :1477 (fused sweep + device FPS + eval)
+  Fusion.rigid_tracking(...)                           reference fusion.py:1608 (tracking.FusedRigidTracker, one CUDA graph)
   Fusion.curr_obs_torch                                reference fusion.py:210-215, 707-714
 
 Same names, argument meaning, return dict and error behaviour.  What differs:
@@ -472,6 +474,83 @@ class Fusion:
         if dense:
             res_d['dist'], res_d['valid_mask'] = dist, valid
         return res_d
+
+    # ------------------------------------------------------------------ callers of the path, kept as thin mirrors -----
+    @staticmethod
+    def farthest_point_sample(pts, n, init_idx=-1, generator=None):
+        """Farthest-point sampling of `n` of the (M,3) device points (the role of utils/my_utils.py fps_np in the
+        reference, fusion.py:1446): greedy max-min distance from a start point (init_idx, or random when -1).
+        Runs on the device; returns (samples (n,3), indices (n,))."""
+        M = int(pts.shape[0])
+        assert M > 0
+        n = int(n)
+        start = int(init_idx) if init_idx != -1 else int(torch.randint(M, (1,), generator=generator).item())
+        idx = torch.empty(n, dtype=torch.long, device=pts.device)
+        idx[0] = start
+        d = (pts - pts[start]).norm(dim=1)
+        for k in range(1, n):
+            j = torch.argmax(d)
+            idx[k] = j
+            d = torch.minimum(d, (pts - pts[j]).norm(dim=1))
+        return pts[idx], idx
+
+    def _select_features(self, cand, N, per_instance, init_idx, name='dino_feats'):
+        """The per-instance loop of select_features_rand / select_features_from_pcd (fusion.py:1441-1451): for every
+        instance i >= 1 (consecutive repeats of a label skipped unless per_instance) farthest-point-sample N of its
+        candidates and evaluate their descriptors."""
+        label = self.curr_obs_torch.get('consensus_mask_label')
+        num_inst = int(self.curr_obs_torch['mask'].shape[-1])
+        if label is None:
+            label = [str(i) for i in range(num_inst)]
+        feats, pts_out = [], []
+        last_label = label[0]
+        for i in range(1, len(label)):
+            if label[i] == last_label and not per_instance:
+                continue
+            sel = cand['pts'][cand['inst'] == i]
+            if sel.shape[0] == 0:                       # select_features_from_pcd skips empty instances (fusion.py:1504)
+                last_label = label[i]
+                continue
+            sample, _ = self.farthest_point_sample(sel, N, init_idx)
+            feats.append(self.eval(sample, return_names=[name])[name])
+            pts_out.append(sample.cpu().numpy())
+            last_label = label[i]
+        return feats, pts_out, []                       # (src_feats_list, src_pts_list, img_list: drawing is out of scope)
+
+    def select_features_rand(self, boundaries, N, per_instance=False, res=None, init_idx=-1):
+        """Reference fusion.py:1418-1475: N descriptors per instance from a `res`-spaced sweep of `boundaries`
+        (default 1 mm: 101 M voxels).  The sweep, the thresholds and the selection are ONE fused launch (sweep_select);
+        FPS and the descriptor evaluation of the N samples follow on the device.  Returns (src_feats_list,
+        src_pts_list, img_list) like the reference; img_list is empty (keypoint drawing is visualisation)."""
+        cand = self.sweep_select(boundaries, 0.001 if res is None else res)
+        return self._select_features(cand, N, per_instance, init_idx)
+
+    def select_features_from_pcd(self, pcd, N, per_instance=False, init_idx=-1, vis=False):
+        """Reference fusion.py:1477-1537: the same selection over an explicit (M,3) point cloud (numpy or tensor)."""
+        dev = self.curr_obs_torch['depth'].device
+        pts = _as_device(pcd, dev, torch.float32).contiguous()
+        cand = self.sweep_select(pts=pts)
+        return self._select_features(cand, N, per_instance, init_idx)
+
+    def rigid_tracking(self, src_feat_info, last_match_pts_list, boundaries, rand_ptcl_num, iters=100):
+        """Reference fusion.py:1608-1685: per-instance rigid pose by 100 Adam iterations through eval.  One CUDA-graph
+        replay (tracking.FusedRigidTracker: 4 launches per iteration); the observation tensors are captured by address,
+        so the graph is rebuilt when update() has replaced them.  Returns {'match_pts_list': [...]} like the reference."""
+        from .tracking import FusedRigidTracker
+        dev = self.curr_obs_torch['depth'].device
+        src = torch.cat([src_feat_info[k]['src_feats'] for k in src_feat_info.keys()], dim=0).to(dev, torch.float32)
+        num_inst = len(last_match_pts_list)
+        last = torch.from_numpy(np.stack(last_match_pts_list, axis=0)).to(dev, torch.float32)
+        assert tuple(last.shape[:2]) == (num_inst, rand_ptcl_num)
+        key = (num_inst, int(rand_ptcl_num), int(src.shape[1]), int(iters),
+               tuple(int(self.curr_obs_torch[k].data_ptr()) for k in ('pose', 'K', 'depth', 'dino_feats')))
+        tr = getattr(self, '_tracker', None)
+        if tr is None or getattr(self, '_tracker_key', None) != key:
+            tr = self._tracker = FusedRigidTracker(self, num_inst, int(rand_ptcl_num), int(src.shape[1]), iters=iters)
+            self._tracker_key = key
+        res = tr.track(src, last)
+        m = res['match_pts'].cpu().numpy()
+        return {'match_pts_list': [m[i] for i in range(num_inst)]}
 
     def eval_pca(self, pts, name, mean, components):
         """eval(pts, [name])[name] followed by sklearn's PCA.transform, (row - mean) @ components.T (what the

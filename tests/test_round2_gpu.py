@@ -250,3 +250,37 @@ def test_eval_host_from_two_threads_at_once():
             assert torch.equal(got[i][k], want[i][k].cpu()), (i, k)
     _native.release_scratch()
     assert torch.equal(f.eval_host(pts[0], ['mask'])['mask'], want[0]['mask'].cpu())
+
+
+# ---------------------------------------------------------------------------- thin mirrors of the path's callers
+def test_select_features_and_rigid_tracking_mirrors():
+    """select_features_rand / select_features_from_pcd / rigid_tracking keep the reference's signatures and return
+    shapes (fusion.py:1418, 1477, 1608) on top of the fused sweep and the graph tracker."""
+    sc = S.make_scene(4, 240, 320, seed=77, feat=(24, 32, 64), num_inst=4)
+    f = make_fusion(sc, DEV, mask_u8=True)
+    f.curr_obs_torch['consensus_mask_label'] = ['background', 'mug', 'mug', 'fork']
+    b = dict(x_lower=-0.3, x_upper=0.3, y_lower=-0.3, y_upper=0.3, z_lower=-0.15, z_upper=0.28)
+    feats, pts, imgs = f.select_features_rand(b, 20, per_instance=True, res=0.004, init_idx=0)
+    assert len(feats) == len(pts) == 3 and imgs == []
+    for ft, p in zip(feats, pts):
+        assert tuple(ft.shape) == (20, 64) and p.shape == (20, 3) and len(np.unique(p, axis=0)) == 20
+        o = f.eval(torch.from_numpy(p).to(DEV), return_names=['mask'])
+        assert (o['dist'].abs() < 0.005).all() and o['valid_mask'].all()           # every sample passed the reference's test
+    feats2, pts2, _ = f.select_features_rand(b, 20, per_instance=False, res=0.004, init_idx=0)
+    assert len(feats2) == 2                                  # the repeated 'mug' label is skipped (fusion.py:1442)
+    cloud = np.concatenate(pts, 0).repeat(3, 0) + np.random.RandomState(0).normal(0, 0.0005, (180, 3)).astype(np.float32)
+    feats3, pts3, _ = f.select_features_from_pcd(cloud.astype(np.float32), 5, per_instance=True, init_idx=0)
+    assert all(tuple(x.shape) == (5, 64) for x in feats3) and len(feats3) >= 1
+    # farthest-point sampling: greedy max-min distances are non-increasing
+    pc = torch.from_numpy(S.scattered_points(2000, 1)).to(DEV)
+    smp, idx = f.farthest_point_sample(pc, 50, init_idx=3)
+    assert idx[0].item() == 3 and len(set(idx.tolist())) == 50
+    dmin = [float((smp[:k] - smp[k]).norm(dim=1).min()) for k in range(1, 50)]
+    assert all(dmin[i] >= dmin[i + 1] - 1e-6 for i in range(len(dmin) - 1))
+    # rigid_tracking: reference signature in, {'match_pts_list': [...]} out
+    info = {'mug': {'src_feats': feats[0]}, 'fork': {'src_feats': feats[2]}}
+    out = f.rigid_tracking(info, [pts[0] + 0.002, pts[2] - 0.002], b, 20, iters=30)
+    assert len(out['match_pts_list']) == 2 and out['match_pts_list'][0].shape == (20, 3)
+    assert np.isfinite(out['match_pts_list'][1]).all()
+    out2 = f.rigid_tracking(info, [pts[0] + 0.002, pts[2] - 0.002], b, 20, iters=30)     # same graph, same answer
+    assert np.array_equal(out['match_pts_list'][0], out2['match_pts_list'][0])
