@@ -92,6 +92,26 @@ def _worker(rank, world, port, q):
                 comm.check()
                 assert torch.equal(got['dist'], full['dist'][:len(sub)]) and torch.equal(got['valid_mask'], full['valid_mask'][:len(sub)])
                 del m
+        # stress: 600 back-to-back steps alternating between two point sets, every step's gathered arrays compared on
+        # the device.  A stale or late remote store (an ordering hole in the per-CTA gpu-scope fence / last-CTA
+        # system fence protocol) would show up as a mismatch against the set of THAT step.
+        if comm is not None:
+            big = torch.from_numpy(S.grid_points(32 * world, 50, 50)).to(dev)       # thousands of CTAs per rank and step
+            comm.close()
+            comm = SH.make_peer_comm(len(big), device=dev, staging_bytes=0)
+            assert comm is not None
+            sets = [big, (big + torch.tensor([0.003, -0.002, 0.001], device=dev)).contiguous()]
+            truth = [f.eval(s_, return_names=[]) for s_ in sets]
+            shares = [SH.plan_share(s_, block=50 * 50) for s_ in sets]
+            bad = torch.zeros((), dtype=torch.int64, device=dev)
+            for step in range(600):
+                k = step & 1
+                got = SH.eval_sharded(f.eval, None, [], comm=comm, share=shares[k])
+                bad += (got['dist'] != truth[k]['dist']).sum() + (got['valid_mask'] != truth[k]['valid_mask']).sum()
+            comm.check()
+            assert int(bad.item()) == 0, f'{int(bad.item())} stale / wrong gathered entries over 600 steps'
+            assert not torch.equal(truth[0]['dist'], truth[1]['dist'])
+            report['stress_steps'] = 600
         if comm is not None:
             comm.close()
         report['ok'] = True
