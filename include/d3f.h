@@ -67,7 +67,7 @@ typedef struct D3FObs {
 
 /* One sampled map of return_names: Fusion.curr_obs_torch[name] (reference fusion.py:372-379). */
 typedef struct D3FKey {
-    const void* data;     /* (V,h,w,C) channels-last, contiguous */
+    const void* data;     /* (V,h,w,C) channels-last; contiguous unless the strides below say otherwise */
     int32_t dtype;        /* D3F_F32 | D3F_U8 */
     int32_t h, w, C;
     int64_t stride_v, stride_y, stride_x;
@@ -75,7 +75,9 @@ typedef struct D3FKey {
                              (h*w*C, w*C, C).  The channel axis always has stride 1 (what makes the gather
                              coalesced).  Lets a caller pass a crop or a padded map without a copy: the
                              reference samples a permuted *view* of its (V,h,w,C) tensor (fusion.py:373).
-                             When C % 4 == 0 every stride must be a multiple of 4 elements. */
+                             Strides that are multiples of 4 elements (and C % 4 == 0) keep the 128-bit
+                             loads; otherwise the map is read with scalar loads.  One view may span at most
+                             2^31 - 1 elements. */
     const float* bias;    /* NULL, or (C) device floats subtracted from every output row (C < 128 only).
                              Used for PCA'd descriptor fields: because the field is linear in the sampled map,
                              (field - mean) @ W^T == field_of(map @ W^T) - mean @ W^T, so the map is projected
