@@ -170,7 +170,7 @@ struct ViewSample {
 template <bool RECIP>
 __device__ __forceinline__ ViewSample view_sample(const float Hm[12], float x, float y, float z,
                                                   const float* __restrict__ depth_v, int H, int W,
-                                                  float mu, bool eval_dist) {
+                                                  float mu, bool eval_dist, bool need_weight = true) {
     ViewSample s;
     float cx = hdot(Hm + 0, x, y, z);
     float cy = hdot(Hm + 4, x, y, z);
@@ -191,8 +191,11 @@ __device__ __forceinline__ ViewSample view_sample(const float Hm[12], float x, f
         s.weight = 1.f;
     } else {
         s.vis = (dep > 0.f) && ok && (s.d > -mu);   // fusion.py:344
-        float a = fminf(__fsub_rn(mu, fabsf(s.d)), 0.f);
-        s.weight = expf(__fdiv_rn(a, mu));          // fusion.py:347
+        s.weight = 1.f;
+        if (need_weight) {                          // launches without keys (dist / valid_mask only) never read it
+            float a = fminf(__fsub_rn(mu, fabsf(s.d)), 0.f);
+            s.weight = expf(__fdiv_rn(a, mu));      // fusion.py:347
+        }
     }
     return s;
 }

@@ -84,7 +84,7 @@ field_sweep_kernel(const EvalParams ep, const SweepParams sp) {
     float acc = 0.f, cnt = 0.f;
     if (live) {
         for (int v = 0; v < V; ++v) {
-            const ViewSample s = view_sample<RECIP>(sH + v * 12, x, y, z, ep.depth + (size_t)v * ep.H * ep.W, ep.H, ep.W, ep.mu, false);
+            const ViewSample s = view_sample<RECIP>(sH + v * 12, x, y, z, ep.depth + (size_t)v * ep.H * ep.W, ep.H, ep.W, ep.mu, false, false);
             if (s.vis) {
                 acc = __fadd_rn(acc, fminf(fmaxf(s.d, -ep.mu), ep.mu));
                 cnt = __fadd_rn(cnt, 1.f);

@@ -353,7 +353,8 @@ field_tile_kernel(const EvalParams ep, const KeySet ks) {
         float Hm[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) Hm[j] = sm.H[v * 12 + j];
-        ViewSample smp = view_sample<RECIP>(Hm, x, y, z, ep.depth + (size_t)v * ep.H * ep.W, ep.H, ep.W, ep.mu, eval_dist);
+        ViewSample smp = view_sample<RECIP>(Hm, x, y, z, ep.depth + (size_t)v * ep.H * ep.W, ep.H, ep.W, ep.mu, eval_dist,
+                                            ks.n_keys > 0);
         const int s = p * NV + v;
         sm.px[s] = smp.px; sm.py[s] = smp.py;
         sm.d[s] = eval_dist ? smp.d : fminf(fmaxf(smp.d, -ep.mu), ep.mu);    // fusion.py:358
