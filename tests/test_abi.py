@@ -82,3 +82,20 @@ def test_kernel_resource_contract():
     assert 'REDUX.OR' in tile, 'uniform mask reduction missing'
     assert 'STG.E.EF.128' in tile, '128-bit streaming (evict-first) row stores missing'
     assert tile.count('LDG.E.EL.128.CONSTANT') >= 16, 'L1 evict-last 128-bit texel loads missing'
+
+
+def test_integration_stub_matches_the_struct_layouts():
+    """INTEGRATION.md shows the ctypes structs a maintainer of the reference would paste into fusion.py: their field
+    names and order must be the binding's (and therefore the header's)."""
+    md = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    def fields(cls):
+        body = md[md.index(f'class {cls}(C.Structure)'):]
+        body = body[:body.index('\n\n')]
+        return re.findall(r"\('([a-zA-Z_]+)',", body)
+    assert fields('_Obs') == [n for n, _ in _native.D3FObs._fields_]
+    assert fields('_Key') == [n for n, _ in _native.D3FKey._fields_]
+    hdr = open(os.path.join(ROOT, 'include', 'd3f.h')).read()
+    key = hdr[hdr.index('typedef struct D3FKey {'):hdr.index('} D3FKey;')]
+    key = re.sub(r'/\*.*?\*/', '', key, flags=re.S)
+    names = re.findall(r'\b([a-zA-Z_]+)\s*(?:,|;)', key)
+    assert names == [n for n, _ in _native.D3FKey._fields_], names
