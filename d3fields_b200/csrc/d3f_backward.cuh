@@ -109,6 +109,9 @@ field_backward_kernel(const EvalParams ep, const BwdKeySet ks, const float* __re
             if (ks.vec4[k]) {
                 // wide float32 maps (the 1024-channel descriptors): one 128-bit load per corner and lane
                 const float* vol = static_cast<const float*>(ks.data[k]);
+                // unrolled by two: the five 128-bit loads of two 128-channel steps are issued together (half the L2 round
+                // trips — a tracking launch is a few hundred warps, nothing else hides the latency)
+#pragma unroll 2
                 for (int c = lane * 4; c < C; c += 128) {
                     float4 f00 = __ldg(reinterpret_cast<const float4*>(vol + o00 + c));
                     float4 f01 = __ldg(reinterpret_cast<const float4*>(vol + o01 + c));
