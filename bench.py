@@ -88,6 +88,14 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def wait_started(self, timeout=15.0):
+        """nvidia-smi can take more than a second to print its first row on an 8-GPU box: do not start the load before
+        it is sampling, or the (short) timed region is over before the first sample."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+        return bool(self.rows)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
@@ -438,14 +446,19 @@ def main():
         return SH.eval_sharded(f.eval, pts_full, names, gather=('dist', 'valid_mask'), share=share)
 
     clk = ClockSampler(local)
-    clk.__enter__()                    # samples cover the warm-up and the timed region (the latter lasts ~20 ms)
+    if rank == 0:
+        clk.__enter__()                # samples cover the warm-up, the load loop and the timed region (~20 ms)
+        clk.wait_started()
+        clk.rows.clear()               # keep only samples taken under load
+    if world > 1:
+        dist.barrier()
     for _ in range(args.warmup):
         out = step()
         flush.zero_()
     torch.cuda.synchronize(dev)
     # Keep the GPU under this load for ~0.5 s so nvidia-smi samples it.  The count is FIXED, never time-based: every
     # step contains a collective at N > 1, so all ranks must run exactly the same number of steps.
-    for _ in range(int(os.environ.get('D3F_BENCH_LOAD_STEPS', '300'))):      # (shortened under ncu: a launch list of 600 warm-up kernels helps nobody)
+    for _ in range(int(os.environ.get('D3F_BENCH_LOAD_STEPS', '600'))):      # (shortened under ncu: a launch list of 600 warm-up kernels helps nobody)
         out = step()
         flush.zero_()
     torch.cuda.synchronize(dev)
@@ -465,7 +478,8 @@ def main():
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
-    clk.__exit__(None, None, None)
+    if rank == 0:
+        clk.__exit__(None, None, None)
     launches = _native.launch_count() - launches0
     if comm is not None:
         comm.check()
