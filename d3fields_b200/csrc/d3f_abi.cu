@@ -688,10 +688,15 @@ int d3f_eval_backward(const D3FObs* obs, const float* pts, int64_t n, const D3FK
     const int64_t blocks = (n + d3f::BWD_WARPS - 1) / d3f::BWD_WARPS;
     if (blocks > 0x7fffffffll) return fail(D3F_EINVAL, "backward: n too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (flags & D3F_FLAG_RECIP_NORM)
+    const bool recip = (flags & D3F_FLAG_RECIP_NORM) != 0;
+    if (n <= d3f::BWD_SPLIT_MAX) {               // latency path: one CTA per point, views dealt to its warps
+        if (recip) d3f::field_backward_split_kernel<true><<<(unsigned)n, d3f::BWD_WARPS * 32, 0, st>>>(ep, ks, grad_dist, grad_pts);
+        else       d3f::field_backward_split_kernel<false><<<(unsigned)n, d3f::BWD_WARPS * 32, 0, st>>>(ep, ks, grad_dist, grad_pts);
+    } else if (recip) {
         d3f::field_backward_kernel<true><<<(unsigned)blocks, d3f::BWD_WARPS * 32, 0, st>>>(ep, ks, grad_dist, grad_pts);
-    else
+    } else {
         d3f::field_backward_kernel<false><<<(unsigned)blocks, d3f::BWD_WARPS * 32, 0, st>>>(ep, ks, grad_dist, grad_pts);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     D3F_CUDA(cudaGetLastError());
     return D3F_OK;

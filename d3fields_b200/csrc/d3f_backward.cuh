@@ -35,53 +35,11 @@ struct BwdKeySet {
     int32_t n_keys;
 };
 
+// d loss / d pts contributed by ONE visible view v of point i (all 32 lanes of a warp take part: they stride the
+// channels); the result is valid in every lane.  sv = {px, py, cz, d, weight}, inv = 1/(count+1e-6), gd = d loss/d dist.
 template <bool RECIP>
-__global__ void __launch_bounds__(BWD_WARPS * 32)
-field_backward_kernel(const EvalParams ep, const BwdKeySet ks, const float* __restrict__ grad_dist,
-                      float* __restrict__ grad_pts) {
-    __shared__ float sH[D3F_MAX_VIEWS * 12];
-    __shared__ float s_view[BWD_WARPS][D3F_MAX_VIEWS][8];   // px, py, cz, d, weight, vis, (unused x2)
-    const int V = ep.V;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = threadIdx.x; r < V * 3; r += BWD_WARPS * 32) {
-        const int v = r / 3, i = r - v * 3;
-        float row[4];
-        krt_row(ep.K + v * 9, ep.pose + v * 12, i, row);
-        sH[v * 12 + i * 4 + 0] = row[0]; sH[v * 12 + i * 4 + 1] = row[1];
-        sH[v * 12 + i * 4 + 2] = row[2]; sH[v * 12 + i * 4 + 3] = row[3];
-    }
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * BWD_WARPS + warp;
-    if (i >= ep.n) return;
-    const float x = __ldg(ep.pts + i * 3), y = __ldg(ep.pts + i * 3 + 1), z = __ldg(ep.pts + i * 3 + 2);
-
-    // per-view forward, one lane per view
-    bool vis = false;
-    if (lane < V) {
-        float Hm[12];
-#pragma unroll
-        for (int j = 0; j < 12; ++j) Hm[j] = sH[lane * 12 + j];
-        const ViewSample sm = view_sample<RECIP>(Hm, x, y, z, ep.depth + (size_t)lane * ep.H * ep.W, ep.H, ep.W, ep.mu, false);
-        vis = sm.vis;
-        float* sv = s_view[warp][lane];
-        sv[0] = sm.px; sv[1] = sm.py;
-        sv[2] = hdot(Hm + 8, x, y, z);           // camera z (a visible view never has the |z|<1e-4 patch)
-        sv[3] = sm.d; sv[4] = sm.weight; sv[5] = vis ? 1.f : 0.f;
-    }
-    const unsigned vis_mask = __ballot_sync(0xffffffffu, vis);
-    const float cnt = (float)__popc(vis_mask);
-    __syncwarp();
-    if (cnt == 0.f) {                            // no view sees the point: every output is a constant
-        if (lane < 3) grad_pts[i * 3 + lane] = 0.f;
-        return;
-    }
-    const float inv = __fdiv_rn(1.f, __fadd_rn(cnt, 1e-6f));
-    const float gd = grad_dist ? __ldg(grad_dist + i) : 0.f;
-
-    float gx = 0.f, gy = 0.f, gz = 0.f;          // accumulated by lane 0
-    for (int v = 0; v < V; ++v) {
-        if (!(vis_mask & (1u << v))) continue;
-        const float* sv = s_view[warp][v];
+__device__ __forceinline__ float3 view_gradient(const EvalParams& ep, const BwdKeySet& ks, int64_t i, int v,
+                                                const float* sv, float inv, float gd, const float* sH, int lane) {
         const float px = sv[0], py = sv[1], cz = sv[2], d = sv[3], weight = sv[4];
         const float fac = weight * inv;
         float G_px = 0.f, G_py = 0.f, G_w = 0.f;
@@ -166,12 +124,121 @@ field_backward_kernel(const EvalParams ep, const BwdKeySet ks, const float* __re
         const float G_cx = G_px / cz, G_cy = G_py / cz;
         const float G_cz = -G_d - (G_px * px + G_py * py) / cz;
         const float* Hm = sH + v * 12;
-        gx += Hm[0] * G_cx + Hm[4] * G_cy + Hm[8] * G_cz;
-        gy += Hm[1] * G_cx + Hm[5] * G_cy + Hm[9] * G_cz;
-        gz += Hm[2] * G_cx + Hm[6] * G_cy + Hm[10] * G_cz;
+        return make_float3(Hm[0] * G_cx + Hm[4] * G_cy + Hm[8] * G_cz,
+                           Hm[1] * G_cx + Hm[5] * G_cy + Hm[9] * G_cz,
+                           Hm[2] * G_cx + Hm[6] * G_cy + Hm[10] * G_cz);
+}
+
+template <bool RECIP>
+__global__ void __launch_bounds__(BWD_WARPS * 32)
+field_backward_kernel(const EvalParams ep, const BwdKeySet ks, const float* __restrict__ grad_dist,
+                      float* __restrict__ grad_pts) {
+    __shared__ float sH[D3F_MAX_VIEWS * 12];
+    __shared__ float s_view[BWD_WARPS][D3F_MAX_VIEWS][8];   // px, py, cz, d, weight, vis, (unused x2)
+    const int V = ep.V;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = threadIdx.x; r < V * 3; r += BWD_WARPS * 32) {
+        const int v = r / 3, i = r - v * 3;
+        float row[4];
+        krt_row(ep.K + v * 9, ep.pose + v * 12, i, row);
+        sH[v * 12 + i * 4 + 0] = row[0]; sH[v * 12 + i * 4 + 1] = row[1];
+        sH[v * 12 + i * 4 + 2] = row[2]; sH[v * 12 + i * 4 + 3] = row[3];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * BWD_WARPS + warp;
+    if (i >= ep.n) return;
+    const float x = __ldg(ep.pts + i * 3), y = __ldg(ep.pts + i * 3 + 1), z = __ldg(ep.pts + i * 3 + 2);
+
+    // per-view forward, one lane per view
+    bool vis = false;
+    if (lane < V) {
+        float Hm[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) Hm[j] = sH[lane * 12 + j];
+        const ViewSample sm = view_sample<RECIP>(Hm, x, y, z, ep.depth + (size_t)lane * ep.H * ep.W, ep.H, ep.W, ep.mu, false);
+        vis = sm.vis;
+        float* sv = s_view[warp][lane];
+        sv[0] = sm.px; sv[1] = sm.py;
+        sv[2] = hdot(Hm + 8, x, y, z);           // camera z (a visible view never has the |z|<1e-4 patch)
+        sv[3] = sm.d; sv[4] = sm.weight; sv[5] = vis ? 1.f : 0.f;
+    }
+    const unsigned vis_mask = __ballot_sync(0xffffffffu, vis);
+    const float cnt = (float)__popc(vis_mask);
+    __syncwarp();
+    if (cnt == 0.f) {                            // no view sees the point: every output is a constant
+        if (lane < 3) grad_pts[i * 3 + lane] = 0.f;
+        return;
+    }
+    const float inv = __fdiv_rn(1.f, __fadd_rn(cnt, 1e-6f));
+    const float gd = grad_dist ? __ldg(grad_dist + i) : 0.f;
+
+    float gx = 0.f, gy = 0.f, gz = 0.f;          // accumulated by lane 0
+    for (int v = 0; v < V; ++v) {
+        if (!(vis_mask & (1u << v))) continue;
+        const float3 c = view_gradient<RECIP>(ep, ks, i, v, s_view[warp][v], inv, gd, sH, lane);
+        gx += c.x; gy += c.y; gz += c.z;
     }
     if (lane == 0) {
         grad_pts[i * 3 + 0] = gx; grad_pts[i * 3 + 1] = gy; grad_pts[i * 3 + 2] = gz;
+    }
+}
+
+// The same gradient with one CTA per point and the views dealt to its warps: a tracking launch is a few hundred points
+// (reference fusion.py:1650), and with one warp per point each warp walks its views — and their L2 round trips — one
+// after the other.  Here the four (or more) views of a point are in flight at once; thread 0 adds the per-view
+// contributions in view order, like the kernel above.  Used for launches of up to BWD_SPLIT_MAX points.
+constexpr int BWD_SPLIT_MAX = 8192;
+
+template <bool RECIP>
+__global__ void __launch_bounds__(BWD_WARPS * 32)
+field_backward_split_kernel(const EvalParams ep, const BwdKeySet ks, const float* __restrict__ grad_dist,
+                            float* __restrict__ grad_pts) {
+    __shared__ float sH[D3F_MAX_VIEWS * 12];
+    __shared__ float s_view[D3F_MAX_VIEWS][8];
+    __shared__ float s_c[D3F_MAX_VIEWS][3];
+    const int V = ep.V;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = threadIdx.x; r < V * 3; r += BWD_WARPS * 32) {
+        const int v = r / 3, k = r - v * 3;
+        float row[4];
+        krt_row(ep.K + v * 9, ep.pose + v * 12, k, row);
+        sH[v * 12 + k * 4 + 0] = row[0]; sH[v * 12 + k * 4 + 1] = row[1];
+        sH[v * 12 + k * 4 + 2] = row[2]; sH[v * 12 + k * 4 + 3] = row[3];
+    }
+    __syncthreads();
+    const int64_t i = blockIdx.x;
+    const float x = __ldg(ep.pts + i * 3), y = __ldg(ep.pts + i * 3 + 1), z = __ldg(ep.pts + i * 3 + 2);
+    if (threadIdx.x < V) {                       // per-view forward, one thread per view
+        const int v = threadIdx.x;
+        float Hm[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) Hm[j] = sH[v * 12 + j];
+        const ViewSample sm = view_sample<RECIP>(Hm, x, y, z, ep.depth + (size_t)v * ep.H * ep.W, ep.H, ep.W, ep.mu, false);
+        float* sv = s_view[v];
+        sv[0] = sm.px; sv[1] = sm.py;
+        sv[2] = hdot(Hm + 8, x, y, z);
+        sv[3] = sm.d; sv[4] = sm.weight; sv[5] = sm.vis ? 1.f : 0.f;
+    }
+    __syncthreads();
+    float cnt = 0.f;
+    for (int v = 0; v < V; ++v) cnt += s_view[v][5];
+    if (cnt == 0.f) {                            // no view sees the point: every output is a constant
+        if (threadIdx.x < 3) grad_pts[i * 3 + threadIdx.x] = 0.f;
+        return;
+    }
+    const float inv = __fdiv_rn(1.f, __fadd_rn(cnt, 1e-6f));
+    const float gd = grad_dist ? __ldg(grad_dist + i) : 0.f;
+    for (int v = warp; v < V; v += BWD_WARPS) {
+        float3 c = make_float3(0.f, 0.f, 0.f);
+        if (s_view[v][5] != 0.f) c = view_gradient<RECIP>(ep, ks, i, v, s_view[v], inv, gd, sH, lane);
+        if (lane == 0) { s_c[v][0] = c.x; s_c[v][1] = c.y; s_c[v][2] = c.z; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float g = 0.f;
+        for (int v = 0; v < V; ++v)
+            if (s_view[v][5] != 0.f) g += s_c[v][threadIdx.x];
+        grad_pts[i * 3 + threadIdx.x] = g;
     }
 }
 
