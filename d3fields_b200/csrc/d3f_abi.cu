@@ -117,8 +117,8 @@ void launch_tile(bool ordered, dim3 grid, dim3 block, cudaStream_t st, const d3f
 }
 
 // NV = 4: up to four views (every configuration the reference runs).  NV = 8: five to eight views.  NV = 0: four view
-// slots with 32-point tiles, for launches too small to fill the GPU with 256-point tiles (latency: a warp walks its
-// tile serially).  The lookahead prefetch variant is instantiated for NV = 4 only.
+// slots with 32-point tiles (NV = 1: 8-point tiles), for launches too small to fill the GPU with 256-point tiles
+// (latency: a warp walks its tile serially).  The lookahead prefetch variant is instantiated for NV = 4 only.
 template <int NV>
 void launch_tile_nv(bool recip, bool wide, bool prefetch, bool ordered, dim3 grid, dim3 block, cudaStream_t st,
                     const d3f::EvalParams& ep, const d3f::KeySet& ks) {
@@ -180,9 +180,10 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
     // small launches (tracking: a few hundred points; mesh vertices: tens of thousands) take 32-point tiles; measured
     // crossover between 100 000 points (149 vs 171 us) and 150 000 (208 vs 182 us): profiles/r02_ab_small_tiles.jsonl
     static const int64_t small_n = [] { const char* e = getenv("D3F_SMALL_TILE_N"); return e ? atoll(e) : 100000ll; }();
-    const int nv = obs->V <= 4 ? ((n <= small_n && !order) ? 0 : 4) : 8;
+    static const int64_t tiny_n = [] { const char* e = getenv("D3F_TINY_TILE_N"); return e ? atoll(e) : 2048ll; }();
+    const int nv = obs->V <= 4 ? ((n <= small_n && !order) ? (n <= tiny_n ? 1 : 0) : 4) : 8;
     const int slice = nv == 8 ? d3f::TileGeom<8>::SLICE : d3f::TileGeom<4>::SLICE;
-    const int tile_pts = nv == 0 ? d3f::TileGeom<0>::PTS : (nv == 4 ? d3f::TileGeom<4>::PTS : d3f::TileGeom<8>::PTS);
+    const int tile_pts = nv == 1 ? d3f::TileGeom<1>::PTS : nv == 0 ? d3f::TileGeom<0>::PTS : (nv == 4 ? d3f::TileGeom<4>::PTS : d3f::TileGeom<8>::PTS);
     auto is_wide = [&](int k) {
         return d3f::key_is_wide(keys[k].dtype, keys[k].C, keys[k].h, keys[k].w, ks.k[k].sv, ks.k[k].sy, ks.k[k].sx, slice);
     };
@@ -206,6 +207,7 @@ int launch_eval(const D3FObs* obs, const float* pts, int64_t n, const D3FKey* ke
         const bool prefetch = force >= 0 ? force != 0 : wide_bytes > (size_t)(64u << 20);
         if (nv == 4)      launch_tile_nv<4>(recip, wide_bytes != 0, prefetch, order != nullptr, grid, block, st, ep, ks);
         else if (nv == 0) launch_tile_nv<0>(recip, wide_bytes != 0, false, false, grid, block, st, ep, ks);
+        else if (nv == 1) launch_tile_nv<1>(recip, wide_bytes != 0, false, false, grid, block, st, ep, ks);
         else              launch_tile_nv<8>(recip, wide_bytes != 0, prefetch, order != nullptr, grid, block, st, ep, ks);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         D3F_CUDA(cudaGetLastError());

@@ -42,11 +42,12 @@ constexpr int TILE_MAX_V = 8;            // views the tile kernel handles (more:
 // so a launch of a few hundred points (rigid_tracking evaluates num_inst x 100, fusion.py:1650; select_features_* a few
 // hundred samples, fusion.py:1449) would put ~10 us of serial walk on two CTAs with 256-point tiles; 32-point tiles
 // spread it over 8x as many CTAs.
+// NVX = 1: the same with 8-point tiles, for launches of at most a few thousand points (one Adam iteration of tracking).
 template <int NVX>
 struct TileGeom {
-    static_assert(NVX == 0 || NVX == 4 || NVX == 8, "view slots per point: 4 or 8 (0: 4 slots, small tiles)");
-    static constexpr int NV = NVX == 0 ? 4 : NVX;
-    static constexpr int PTS = NVX == 0 ? 32 : (NV == 4 ? 256 : 128);   // 256-point tiles beat 128 by 4 % at NV = 4 (fewer barriers and cold starts)
+    static_assert(NVX == 0 || NVX == 1 || NVX == 4 || NVX == 8, "view slots per point: 4 or 8 (0 / 1: 4 slots, small / tiny tiles)");
+    static constexpr int NV = NVX <= 1 ? 4 : NVX;
+    static constexpr int PTS = NVX == 1 ? 8 : NVX == 0 ? 32 : (NV == 4 ? 256 : 128);   // 256-point tiles beat 128 by 4 % at NV = 4 (fewer barriers and cold starts)
     static constexpr int LOG_NV = NV == 4 ? 2 : 3;
     static constexpr int LANE_CH = NV == 4 ? 4 : 2;      // channels per lane: the register cache is NV x 4 corners x LANE_CH = 64
     static constexpr int SLICE = 32 * LANE_CH;           // channels a warp owns

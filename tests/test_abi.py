@@ -73,7 +73,7 @@ def test_kernel_resource_contract():
                         r"(\d+) bytes spill loads\nptxas info\s*: Used (\d+) registers", log)
     assert len(blocks) >= 28, 'expected 28 instantiations of field_tile_kernel in the ptxas log'
     for name, stack, st, ld, regs in blocks:
-        wide = re.search(r'field_tile_kernelILb[01]ELi\d+ELb1ELb[01]ELi[048]EEE', name) is not None
+        wide = re.search(r'field_tile_kernelILb[01]ELi\d+ELb1ELb[01]ELi[0148]EEE', name) is not None
         assert int(st) == 0 and int(ld) == 0, f'{name}: spills'
         assert int(regs) <= (128 if wide else 64), f'{name}: {regs} registers'
     sass = subprocess.run(['cuobjdump', '-sass', build.LIB_PATH], capture_output=True, text=True).stdout
