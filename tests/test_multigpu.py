@@ -86,12 +86,10 @@ def _worker(rank, world, port, q):
                         assert torch.equal(prev['dist'], full['dist'])
                     prev = got
                 # ragged: a different n, ranks with different numbers of points
-                m = n - 7 * rank - 3 if block is None else n
                 sub = pts[:n - 37] if block is None else pts
                 got = SH.eval_sharded(f.eval, sub, [], comm=comm, block=block)
                 comm.check()
                 assert torch.equal(got['dist'], full['dist'][:len(sub)]) and torch.equal(got['valid_mask'], full['valid_mask'][:len(sub)])
-                del m
         # stress: 600 back-to-back steps alternating between two point sets, every step's gathered arrays compared on
         # the device.  A stale or late remote store (an ordering hole in the per-CTA gpu-scope fence / last-CTA
         # system fence protocol) would show up as a mismatch against the set of THAT step.
