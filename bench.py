@@ -329,9 +329,12 @@ def tracking_latency(f, dev, iters=100):
     moved = pts + 0.004
     obs = {k: v for k, v in f.curr_obs_torch.items() if isinstance(v, torch.Tensor)}
     out = {}
-    for name, kw in (('fused_graph', dict(fused=True)), ('graph', dict(graph=True)), ('eager', dict(graph=False)),
+    for name, kw in (('single_launch_graph', dict(fused=1)), ('fused_graph', dict(fused=4)), ('graph', dict(graph=True)),
+                     ('eager', dict(graph=False)),
                      ('torch_reference_ops', dict(graph=False, eval_fn=lambda p, names: TP.eval_chunk(obs, f.H, f.W, p, names)))):
-        tr = FusedRigidTracker(f, I, P, C, iters=iters) if kw.pop('fused', False) else RigidTracker(f, I, P, C, iters=iters, **kw)
+        fused = kw.pop('fused', 0)
+        tr = (FusedRigidTracker(f, I, P, C, iters=iters, single_launch=fused == 1) if fused
+              else RigidTracker(f, I, P, C, iters=iters, **kw))
         tr.track(src, moved)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
@@ -341,7 +344,9 @@ def tracking_latency(f, dev, iters=100):
         torch.cuda.synchronize(dev)
         out[name] = (time.perf_counter() - t0) / reps / iters * 1e6
     return {'points': I * P, 'iterations': iters, 'us_per_iteration': out,
-            'what': 'track() wall time / iterations: forward + backward + Adam step (reference fusion.py:1643-1665). fused_graph: '
+            'what': 'track() wall time / iterations: forward + backward + Adam step (reference fusion.py:1643-1665). '
+                    'single_launch_graph: ONE launch per iteration (d3f_track_step: a CTA per point, texels in registers for '
+                    'forward and backward, the last CTA of an instance takes the Adam step), 100 in one CUDA graph; fused_graph: '
                     '4 launches per iteration (d3f_eval, d3f_track_loss_grad, d3f_eval_backward, d3f_track_update) in one CUDA graph; '
                     'graph / eager: torch autograd around the two field kernels; torch_reference_ops: the reference operator sequence'}
 

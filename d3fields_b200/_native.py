@@ -24,7 +24,7 @@ D3F_ETIMEOUT = -4
 SYMBOLS = ('d3f_eval', 'd3f_eval_host', 'd3f_release_scratch', 'd3f_eval_ordered', 'd3f_bin_workspace_bytes',
            'd3f_bin_order', 'd3f_sweep_select', 'd3f_comm_create', 'd3f_comm_connect', 'd3f_comm_destroy',
            'd3f_comm_status', 'd3f_eval_allgather', 'd3f_comm_broadcast', 'd3f_eval_backward', 'd3f_track_loss_grad',
-           'd3f_track_update', 'd3f_pca_project',
+           'd3f_track_update', 'd3f_track_step_supported', 'd3f_track_step', 'd3f_pca_project',
            'd3f_create_grid', 'd3f_abi_version', 'd3f_last_error', 'd3f_launch_count', 'd3f_last_variant',
            'd3f_sizeof_key', 'd3f_sizeof_obs')
 
@@ -126,6 +126,10 @@ def load() -> C.CDLL:
     lib.d3f_track_loss_grad.restype = C.c_int
     lib.d3f_track_update.argtypes = [C.POINTER(D3FTrack), vp]
     lib.d3f_track_update.restype = C.c_int
+    lib.d3f_track_step_supported.argtypes = [C.POINTER(D3FObs), C.POINTER(D3FKey)]
+    lib.d3f_track_step_supported.restype = C.c_int
+    lib.d3f_track_step.argtypes = [C.POINTER(D3FObs), C.POINTER(D3FKey), vp, C.POINTER(D3FTrack), f32, vp, vp, vp, u32, f32, vp]
+    lib.d3f_track_step.restype = C.c_int
     lib.d3f_sizeof_key.restype = C.c_int
     lib.d3f_sizeof_obs.restype = C.c_int
     lib.d3f_eval_backward.argtypes = [C.POINTER(D3FObs), vp, i64, C.POINTER(D3FKey), i32, C.POINTER(vp), vp, vp, u32, f32, vp]
@@ -286,6 +290,21 @@ def track_update(stream: int, **kw) -> None:
     """d3f_track_update; keyword arguments are the fields of D3FTrack (device addresses / sizes / hyper-parameters)."""
     t = D3FTrack(**kw)
     _check(load().d3f_track_update(C.byref(t), stream))
+
+
+def track_step_supported(V: int, H: int, W: int, pose: int, K: int, depth: int, key: tuple) -> bool:
+    """Whether d3f_track_step (the one-launch Adam iteration) takes this observation / descriptor map."""
+    obs = D3FObs(V, H, W, pose, K, depth)
+    return bool(load().d3f_track_step_supported(C.byref(obs), _keys_array([key])))
+
+
+def track_step(V: int, H: int, W: int, pose: int, K: int, depth: int, key: tuple, src: int, dist_w: float,
+               grad_scratch: int, arrivals: int, loss_terms: Optional[int], flags: int, mu: float, stream: int, **kw) -> None:
+    """d3f_track_step; keyword arguments are the fields of D3FTrack."""
+    obs = D3FObs(V, H, W, pose, K, depth)
+    t = D3FTrack(**kw)
+    _check(load().d3f_track_step(C.byref(obs), _keys_array([key]), src, C.byref(t), dist_w, grad_scratch, arrivals,
+                                 loss_terms, flags, mu, stream))
 
 
 def pca_project(x: int, n: int, c: int, mean: int, comp: int, n_comp: int, y: int, stream: int) -> None:

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>      // header-only; ranges cost nanoseconds when no profiler is attached
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +17,7 @@
 #include "d3f_tile.cuh"
 #include "d3f_aux.cuh"
 #include "d3f_backward.cuh"
+#include "d3f_track.cuh"
 #include "d3f_sweep.cuh"
 #include "d3f_bin.cuh"
 #include "d3f_comm.cuh"
@@ -736,7 +738,70 @@ int d3f_track_update(const D3FTrack* t, void* stream) {
     tp.m_t = t->m_t; tp.v_t = t->v_t; tp.m_r = t->m_r; tp.v_r = t->v_r;
     tp.last_pts = t->last_pts; tp.grad_pts = t->grad_pts; tp.pts = t->pts; tp.I = t->n_inst; tp.P = t->n_pts;
     tp.step = t->step; tp.lr = t->lr; tp.beta1 = t->beta1; tp.beta2 = t->beta2; tp.eps = t->eps; tp.reg_w = t->reg_w;
+    tp.bc1 = (float)(1.0 - pow((double)t->beta1, (double)t->step)); tp.bc2s = (float)sqrt(1.0 - pow((double)t->beta2, (double)t->step));
     d3f::track_update_kernel<<<(unsigned)t->n_inst, d3f::TRACK_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(tp);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    D3F_CUDA(cudaGetLastError());
+    return D3F_OK;
+}
+
+int d3f_track_step_supported(const D3FObs* obs, const D3FKey* key) {
+    if (!obs || !key || !key->data) return 0;
+    if (obs->V < 1 || obs->V > d3f::STEP_VIEWS) return 0;
+    if (key->dtype != D3F_F32 || key->C < 4 || key->C % 4 != 0 || key->C > d3f::STEP_MAX_C) return 0;
+    const KeyStrides ksd = key_strides(*key);
+    if (((ksd.sv | ksd.sy | ksd.sx) & 3) != 0 || !aligned(key->data, 16)) return 0;
+    return 1;
+}
+
+int d3f_track_step(const D3FObs* obs, const D3FKey* key, const float* src, const D3FTrack* t, float dist_w,
+                   float* grad_scratch, uint32_t* arrivals, float* loss_terms, uint32_t flags, float mu, void* stream) {
+    NvtxRange nvtx_("d3f_track_step");
+    if (!obs || !key || !t) return fail(D3F_EINVAL, "track_step: NULL obs / key / track");
+    if (obs->H < 2 || obs->W < 2) return fail(D3F_EINVAL, "image size %dx%d must be at least 2x2", obs->H, obs->W);
+    if (!obs->pose || !obs->K || !obs->depth) return fail(D3F_EINVAL, "obs pose/K/depth pointer is NULL");
+    if (!(mu > 0.f)) return fail(D3F_EINVAL, "mu=%g must be positive", (double)mu);
+    if (flags & ~D3F_FLAG_RECIP_NORM) return fail(D3F_EINVAL, "track_step: unsupported flag bits 0x%x", flags);
+    const int rk = validate_key(*key, 0);
+    if (rk) return rk;
+    if (!d3f_track_step_supported(obs, key))
+        return fail(D3F_EINVAL, "track_step: needs V <= %d and a float32 map with C %% 4 == 0, C <= %d, strides multiples of 4, "
+                    "16-byte aligned (use the four-launch iteration otherwise)", d3f::STEP_VIEWS, d3f::STEP_MAX_C);
+    if (t->n_inst < 0 || t->n_pts < 0 || (int64_t)t->n_inst * t->n_pts >= (1ll << 31)) return fail(D3F_EINVAL, "track_step: bad sizes");
+    if (t->n_inst > 0 && t->n_pts > 0 &&
+        (!src || !grad_scratch || !arrivals || !t->t_in || !t->r_in || !t->t_out || !t->r_out || !t->m_t || !t->v_t || !t->m_r ||
+         !t->v_r || !t->last_pts || t->t_out == t->t_in || t->r_out == t->r_in))
+        return fail(D3F_EINVAL, "track_step: NULL pointer, or output parameters alias the inputs");
+    if (!aligned(src, 16)) return fail(D3F_EINVAL, "track_step: src must be 16-byte aligned");
+    if (!(t->step >= 1.f)) return fail(D3F_EINVAL, "track_step: step=%g must be >= 1", (double)t->step);
+    int rc = check_device();
+    if (rc) return rc;
+    const int64_t n = (int64_t)t->n_inst * t->n_pts;
+    if (n == 0) return D3F_OK;
+    const KeyStrides ksd = key_strides(*key);
+    d3f::TrackStepParams sp;
+    sp.pose = obs->pose; sp.K = obs->K; sp.depth = obs->depth; sp.V = obs->V; sp.H = obs->H; sp.W = obs->W; sp.mu = mu;
+    sp.map = static_cast<const float*>(key->data); sp.h = key->h; sp.w = key->w; sp.C = key->C;
+    sp.sv = ksd.sv; sp.sy = (int32_t)ksd.sy; sp.sx = (int32_t)ksd.sx;
+    sp.src = src; sp.dist_w = dist_w; sp.grad_pts = grad_scratch; sp.loss_terms = loss_terms; sp.arrivals = arrivals;
+    d3f::TrackParams& tp = sp.tp;
+    tp.t_in = t->t_in; tp.r_in = t->r_in; tp.t_out = t->t_out; tp.r_out = t->r_out;
+    tp.m_t = t->m_t; tp.v_t = t->v_t; tp.m_r = t->m_r; tp.v_r = t->v_r;
+    tp.last_pts = t->last_pts; tp.grad_pts = nullptr; tp.pts = t->pts; tp.I = t->n_inst; tp.P = t->n_pts;
+    tp.step = t->step; tp.lr = t->lr; tp.beta1 = t->beta1; tp.beta2 = t->beta2; tp.eps = t->eps; tp.reg_w = t->reg_w;
+    tp.bc1 = (float)(1.0 - pow((double)t->beta1, (double)t->step)); tp.bc2s = (float)sqrt(1.0 - pow((double)t->beta2, (double)t->step));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // one wave if it can be: two CTAs per SM keep everything in registers, three take 1.5x the points at once
+    static const int minb_env = [] { const char* e = getenv("D3F_STEP_MINB"); return e ? atoi(e) : 0; }();            // A/B only
+    const int minb = minb_env ? minb_env : (n <= 2 * 148 ? 2 : 3);
+    const bool recip = (flags & D3F_FLAG_RECIP_NORM) != 0;
+    if (minb == 2) {
+        if (recip) d3f::track_step_kernel<true, 2><<<(unsigned)n, d3f::STEP_THREADS, 0, st>>>(sp);
+        else       d3f::track_step_kernel<false, 2><<<(unsigned)n, d3f::STEP_THREADS, 0, st>>>(sp);
+    } else {
+        if (recip) d3f::track_step_kernel<true, 3><<<(unsigned)n, d3f::STEP_THREADS, 0, st>>>(sp);
+        else       d3f::track_step_kernel<false, 3><<<(unsigned)n, d3f::STEP_THREADS, 0, st>>>(sp);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     D3F_CUDA(cudaGetLastError());
     return D3F_OK;

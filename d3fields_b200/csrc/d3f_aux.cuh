@@ -124,6 +124,7 @@ struct TrackParams {
     float* pts;               // (I*P,3) out: points of the next iteration (nullptr: leave them, e.g. after the last step)
     int I, P;
     float step;               // Adam step number of this update (1, 2, ...)
+    float bc1, bc2s;          // 1 - beta1^step, sqrt(1 - beta2^step)
     float lr, beta1, beta2, eps, reg_w;
 };
 
@@ -145,86 +146,132 @@ __device__ __forceinline__ void so3_exp(const float w[3], float R[9], float& a2_
         }
 }
 
-__global__ void __launch_bounds__(TRACK_THREADS)
-track_update_kernel(const TrackParams tp) {
-    __shared__ float red[TRACK_THREADS / 32][12];
-    __shared__ float sR[9], sT[3];
-    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// One instance's update: reduce d loss / d pts over its points, chain to (t, log_r), regulariser, Adam step into
+// (t_out, r_out); thread 0 leaves the NEW rotation / translation in sR / sT.  Called by all THREADS threads of a CTA.
+// L2_LOADS: grad_pts was written by other CTAs of the SAME launch (track_step_kernel) — read it at the L2.
+// Latency is all that matters here (one CTA, a few hundred flops): thread 0's eighteen scalars are requested before the
+// reduction so their round trip overlaps it (loaded where they are used, each load would queue behind the store of the
+// previous moment — the compiler cannot prove the buffers distinct), the regulariser's norms are reduced by the CTA with
+// the gradient sums, the bias corrections come from the host, and the 3x3 algebra is fully unrolled into registers.
+constexpr int TRACK_RED = 14;
+template <int THREADS, bool L2_LOADS>
+__device__ __forceinline__ void track_update_instance(const TrackParams& tp, int i, float (*red)[TRACK_RED], float* sR, float* sT) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* last = tp.last_pts + (size_t)i * tp.P * 3;
-    if (tp.grad_pts) {
-        // g_t = sum_p g_p ;  M[a][b] = sum_p last_p[a] * g_p[b]   (d loss / d R for pts = last @ R)
-        float acc[12];
+    float w3[3], t3[3], mt[3], vt[3], mr[3], vr[3];
+    if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) acc[k] = 0.f;
-        const float* g = tp.grad_pts + (size_t)i * tp.P * 3;
-        for (int p = tid; p < tp.P; p += TRACK_THREADS) {
-            const float gx = g[p * 3], gy = g[p * 3 + 1], gz = g[p * 3 + 2];
-            const float lx = last[p * 3], ly = last[p * 3 + 1], lz = last[p * 3 + 2];
-            acc[0] += gx; acc[1] += gy; acc[2] += gz;
-            acc[3] += lx * gx; acc[4] += lx * gy; acc[5] += lx * gz;
-            acc[6] += ly * gx; acc[7] += ly * gy; acc[8] += ly * gz;
-            acc[9] += lz * gx; acc[10] += lz * gy; acc[11] += lz * gz;
+        for (int j = 0; j < 3; ++j) {
+            w3[j] = tp.r_in[i * 3 + j]; t3[j] = tp.t_in[i * 3 + j];
+            mt[j] = tp.m_t[i * 3 + j]; vt[j] = tp.v_t[i * 3 + j]; mr[j] = tp.m_r[i * 3 + j]; vr[j] = tp.v_r[i * 3 + j];
         }
+    }
+    // g_t = sum_p g_p ;  M[a][b] = sum_p last_p[a] * g_p[b]   (d loss / d R for pts = last @ R) ;  |t|_F^2, |log_r|_F^2
+    float acc[TRACK_RED];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
+    for (int k = 0; k < TRACK_RED; ++k) acc[k] = 0.f;
+    const float* g = tp.grad_pts + (size_t)i * tp.P * 3;
+    for (int p = tid; p < tp.P; p += THREADS) {
+        const float gx = L2_LOADS ? __ldcg(g + p * 3) : g[p * 3], gy = L2_LOADS ? __ldcg(g + p * 3 + 1) : g[p * 3 + 1];
+        const float gz = L2_LOADS ? __ldcg(g + p * 3 + 2) : g[p * 3 + 2];
+        const float lx = last[p * 3], ly = last[p * 3 + 1], lz = last[p * 3 + 2];
+        acc[0] += gx; acc[1] += gy; acc[2] += gz;
+        acc[3] += lx * gx; acc[4] += lx * gy; acc[5] += lx * gz;
+        acc[6] += ly * gx; acc[7] += ly * gy; acc[8] += ly * gz;
+        acc[9] += lz * gx; acc[10] += lz * gy; acc[11] += lz * gz;
+    }
+    for (int k = tid; k < tp.I * 3; k += THREADS) {       // regulariser: Frobenius norms over ALL instances (fusion.py:1654)
+        const float a = tp.t_in[k], b = tp.r_in[k];
+        acc[12] = fmaf(a, a, acc[12]); acc[13] = fmaf(b, b, acc[13]);
+    }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-            if (lane == 0) red[warp][k] = acc[k];
+    for (int k = 0; k < TRACK_RED; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (lane == 0) red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float G[TRACK_RED];
+#pragma unroll
+        for (int k = 0; k < TRACK_RED; ++k) {
+            G[k] = 0.f;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; ++w) G[k] += red[w][k];
         }
-        __syncthreads();
-        if (tid == 0) {
-            float G[12];
-            for (int k = 0; k < 12; ++k) { G[k] = 0.f; for (int w = 0; w < TRACK_THREADS / 32; ++w) G[k] += red[w][k]; }
-            const float* M = G + 3;
-            float w3[3] = {tp.r_in[i * 3], tp.r_in[i * 3 + 1], tp.r_in[i * 3 + 2]};
-            float t3[3] = {tp.t_in[i * 3], tp.t_in[i * 3 + 1], tp.t_in[i * 3 + 2]};
-            // regulariser: Frobenius norms over all instances (fusion.py:1654)
-            float nt = 0.f, nr = 0.f;
-            for (int k = 0; k < tp.I * 3; ++k) { nt += tp.t_in[k] * tp.t_in[k]; nr += tp.r_in[k] * tp.r_in[k]; }
-            nt = sqrtf(nt); nr = sqrtf(nr);
-            // d R / d w_j  (K = hat(w);  dK_j = hat(e_j))
-            float R[9], a2, f1, f2;
-            so3_exp(w3, R, a2, f1, f2);
-            const float n2 = w3[0] * w3[0] + w3[1] * w3[1] + w3[2] * w3[2];
-            const float a = sqrtf(a2);
-            float df1 = 0.f, df2 = 0.f;                         // d f / d a (zero while the angle is clamped)
-            if (n2 > 1e-4f) {
-                df1 = (a * cosf(a) - sinf(a)) / (a * a);
-                df2 = (a * sinf(a) - 2.f * (1.f - cosf(a))) / (a * a * a);
-            }
-            const float K[9] = {0.f, -w3[2], w3[1], w3[2], 0.f, -w3[0], -w3[1], w3[0], 0.f};
-            float KK[9];
-            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { float s = 0.f; for (int k = 0; k < 3; ++k) s += K[r * 3 + k] * K[k * 3 + c]; KK[r * 3 + c] = s; }
-            float g_w[3], g_t[3];
-            for (int j = 0; j < 3; ++j) {
-                float dK[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (j == 0) { dK[5] = -1.f; dK[7] = 1.f; } else if (j == 1) { dK[2] = 1.f; dK[6] = -1.f; } else { dK[1] = -1.f; dK[3] = 1.f; }
-                const float da = (n2 > 1e-4f) ? w3[j] / a : 0.f;
+        const float* M = G + 3;
+        const float nt = sqrtf(G[12]), nr = sqrtf(G[13]);
+        // d R / d w_j  (K = hat(w);  dK_j = hat(e_j))
+        float R[9], a2, f1, f2;
+        so3_exp(w3, R, a2, f1, f2);
+        const float n2 = w3[0] * w3[0] + w3[1] * w3[1] + w3[2] * w3[2];
+        const float a = sqrtf(a2);
+        float df1 = 0.f, df2 = 0.f;                         // d f / d a (zero while the angle is clamped)
+        if (n2 > 1e-4f) {
+            df1 = (a * cosf(a) - sinf(a)) / (a * a);
+            df2 = (a * sinf(a) - 2.f * (1.f - cosf(a))) / (a * a * a);
+        }
+        const float K[9] = {0.f, -w3[2], w3[1], w3[2], 0.f, -w3[0], -w3[1], w3[0], 0.f};
+        float KK[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
                 float s = 0.f;
-                for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s += K[r * 3 + k] * K[k * 3 + c];
+                KK[r * 3 + c] = s;
+            }
+        float g_w[3], g_t[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float dK[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (j == 0) { dK[5] = -1.f; dK[7] = 1.f; } else if (j == 1) { dK[2] = 1.f; dK[6] = -1.f; } else { dK[1] = -1.f; dK[3] = 1.f; }
+            const float da = (n2 > 1e-4f) ? w3[j] / a : 0.f;
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
                     float dKK = 0.f;
+#pragma unroll
                     for (int k = 0; k < 3; ++k) dKK += dK[r * 3 + k] * K[k * 3 + c] + K[r * 3 + k] * dK[k * 3 + c];
                     const float dR = f1 * dK[r * 3 + c] + f2 * dKK + df1 * da * K[r * 3 + c] + df2 * da * KK[r * 3 + c];
                     s += M[r * 3 + c] * dR;
                 }
-                g_w[j] = s + (nr > 0.f ? tp.reg_w * w3[j] / nr : 0.f);
-                g_t[j] = G[j] + (nt > 0.f ? tp.reg_w * t3[j] / nt : 0.f);
-            }
-            // Adam (torch.optim.Adam, single-tensor path): step_size = lr / (1 - b1^k), denom = sqrt(v)/sqrt(1 - b2^k) + eps
-            const float bc1 = 1.f - powf(tp.beta1, tp.step), bc2s = sqrtf(1.f - powf(tp.beta2, tp.step));
-            const float step_size = tp.lr / bc1;
-            for (int j = 0; j < 3; ++j) {
-                float m = tp.m_t[i * 3 + j] = tp.beta1 * tp.m_t[i * 3 + j] + (1.f - tp.beta1) * g_t[j];
-                float v = tp.v_t[i * 3 + j] = tp.beta2 * tp.v_t[i * 3 + j] + (1.f - tp.beta2) * g_t[j] * g_t[j];
-                t3[j] -= step_size * m / (sqrtf(v) / bc2s + tp.eps);
-                m = tp.m_r[i * 3 + j] = tp.beta1 * tp.m_r[i * 3 + j] + (1.f - tp.beta1) * g_w[j];
-                v = tp.v_r[i * 3 + j] = tp.beta2 * tp.v_r[i * 3 + j] + (1.f - tp.beta2) * g_w[j] * g_w[j];
-                w3[j] -= step_size * m / (sqrtf(v) / bc2s + tp.eps);
-            }
-            for (int j = 0; j < 3; ++j) { tp.t_out[i * 3 + j] = t3[j]; tp.r_out[i * 3 + j] = w3[j]; sT[j] = t3[j]; }
-            float a2n, f1n, f2n;
-            so3_exp(w3, sR, a2n, f1n, f2n);
+            g_w[j] = s + (nr > 0.f ? tp.reg_w * w3[j] / nr : 0.f);
+            g_t[j] = G[j] + (nt > 0.f ? tp.reg_w * t3[j] / nt : 0.f);
         }
+        // Adam (torch.optim.Adam, single-tensor path): step_size = lr / (1 - b1^k), denom = sqrt(v)/sqrt(1 - b2^k) + eps;
+        // bc1 = 1 - b1^k and bc2s = sqrt(1 - b2^k) are computed on the host (d3f_abi.cu)
+        const float step_size = tp.lr / tp.bc1;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            mt[j] = tp.beta1 * mt[j] + (1.f - tp.beta1) * g_t[j];
+            vt[j] = tp.beta2 * vt[j] + (1.f - tp.beta2) * g_t[j] * g_t[j];
+            t3[j] -= step_size * mt[j] / (sqrtf(vt[j]) / tp.bc2s + tp.eps);
+            mr[j] = tp.beta1 * mr[j] + (1.f - tp.beta1) * g_w[j];
+            vr[j] = tp.beta2 * vr[j] + (1.f - tp.beta2) * g_w[j] * g_w[j];
+            w3[j] -= step_size * mr[j] / (sqrtf(vr[j]) / tp.bc2s + tp.eps);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            tp.m_t[i * 3 + j] = mt[j]; tp.v_t[i * 3 + j] = vt[j]; tp.m_r[i * 3 + j] = mr[j]; tp.v_r[i * 3 + j] = vr[j];
+            tp.t_out[i * 3 + j] = t3[j]; tp.r_out[i * 3 + j] = w3[j]; sT[j] = t3[j];
+        }
+        float a2n, f1n, f2n;
+        so3_exp(w3, sR, a2n, f1n, f2n);
+    }
+}
+
+__global__ void __launch_bounds__(TRACK_THREADS)
+track_update_kernel(const TrackParams tp) {
+    __shared__ float red[TRACK_THREADS / 32][TRACK_RED];
+    __shared__ float sR[9], sT[3];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const float* last = tp.last_pts + (size_t)i * tp.P * 3;
+    if (tp.grad_pts) {
+        track_update_instance<TRACK_THREADS, false>(tp, i, red, sR, sT);
     } else if (tid == 0) {
         float w3[3] = {tp.r_in[i * 3], tp.r_in[i * 3 + 1], tp.r_in[i * 3 + 2]};
         float a2, f1, f2;

@@ -141,19 +141,27 @@ class RigidTracker:
 
 
 class FusedRigidTracker:
-    """RigidTracker with every torch op of the iteration replaced by two small kernels (d3f_track_loss_grad,
-    d3f_track_update): one Adam iteration = field query + loss gradient + field backward + pose update = four launches,
-    and the whole `iters`-iteration loop is one CUDA graph.  Same loop, loss, pose parametrisation and Adam arithmetic as
-    RigidTracker / the reference (fusion.py:1633-1665); agreement with the torch-autograd version is checked in
-    tests/test_tracking.py.  The observation (pose, K, depth, the descriptor map) is captured by address: update the
+    """RigidTracker with every torch op of the iteration done by the native library, the whole `iters`-iteration loop one
+    CUDA graph.  Two forms of the iteration:
+      * single_launch (default where d3f_track_step supports the observation: V <= 4, float32 map, C % 4 == 0, C <= 1024):
+        ONE launch per Adam iteration — one CTA per point computes the point from the pose parameters, queries the field,
+        forms the loss gradient and chains it back to the point with the texels held in registers; the last CTA of an
+        instance takes the Adam step (csrc/d3f_track.cuh);
+      * four launches: field query (d3f_eval) + loss gradient (d3f_track_loss_grad) + field backward (d3f_eval_backward) +
+        pose update (d3f_track_update).
+    Same loop, loss, pose parametrisation and Adam arithmetic as RigidTracker / the reference (fusion.py:1633-1665);
+    agreement of both forms with the torch-autograd version is checked in tests/test_tracking.py.  The observation (pose, K, depth, the descriptor map) is captured by address: update the
     tensors of fusion.curr_obs_torch in place between frames, or call invalidate()."""
 
     def __init__(self, fusion, num_instance: int, rand_ptcl_num: int, feat_dim: int, iters: int = 100, lr: float = 0.01,
-                 reg_w: float = 1.0, dist_w: float = 100.0, graph: bool = True, name: str = 'dino_feats'):
+                 reg_w: float = 1.0, dist_w: float = 100.0, graph: bool = True, name: str = 'dino_feats',
+                 single_launch: Optional[bool] = None):
         from . import _native
         self._n = _native
         self.fusion, self.iters, self.lr, self.reg_w, self.dist_w, self.name = fusion, iters, lr, reg_w, dist_w, name
         self.use_graph = graph
+        self.single_launch = single_launch          # None: decided from the observation at the first track()
+        self.launches_per_iteration = None
         dev = torch.device(fusion.device)
         self.dev = dev
         self.I, self.P, self.C = num_instance, rand_ptcl_num, feat_dim
@@ -168,13 +176,15 @@ class FusedRigidTracker:
         self.feat, self.g_feat = z(n, feat_dim), z(n, feat_dim)
         self.dist, self.g_dist, self.loss_terms = z(n), z(n), z(n)
         self.valid = torch.zeros(n, dtype=torch.bool, device=dev)
+        self.arrivals = torch.zeros(num_instance, dtype=torch.int32, device=dev)   # d3f_track_step leaves them zero
         self._graph: Optional[torch.cuda.CUDAGraph] = None
 
     def invalidate(self):
         self._graph = None
+        self.arrivals.zero_()
 
     def _enqueue(self):
-        """The whole loop on torch's current stream: 1 + 4 * iters launches."""
+        """The whole loop on torch's current stream: `iters` launches (single_launch) or 1 + 4 * iters."""
         N, f = self._n, self.fusion
         V, H, W, pose_p, K_p, depth_p = f._obs_ptrs()
         kt, _vol = f._key_tuple(self.name, V)
@@ -184,6 +194,24 @@ class FusedRigidTracker:
         common = dict(m_t=self.m_t.data_ptr(), v_t=self.v_t.data_ptr(), m_r=self.m_r.data_ptr(), v_r=self.v_r.data_ptr(),
                       last_pts=self.last_pts.data_ptr(), n_inst=self.I, n_pts=self.P, lr=self.lr, beta1=0.9, beta2=0.999,
                       eps=1e-8, reg_w=self.reg_w)
+        single = self.single_launch
+        supported = N.track_step_supported(V, H, W, pose_p, K_p, depth_p, kt)
+        if single is None:
+            single = supported
+        elif single and not supported:
+            raise ValueError('single_launch=True: d3f_track_step does not support this observation / descriptor map '
+                             '(needs V <= 4, float32, C % 4 == 0, C <= 1024, aligned)')
+        self.launches_per_iteration = 1 if single else 4
+        if single:
+            for k in range(1, self.iters + 1):
+                a, b = (k - 1) % 2, k % 2
+                N.track_step(V, H, W, pose_p, K_p, depth_p, kt, self.src_feats.data_ptr(), self.dist_w,
+                             self.grad_pts.data_ptr(), self.arrivals.data_ptr(), self.loss_terms.data_ptr(), flags, mu, st,
+                             t_in=self.t[a].data_ptr(), r_in=self.r[a].data_ptr(), t_out=self.t[b].data_ptr(),
+                             r_out=self.r[b].data_ptr(), grad_pts=None,
+                             pts=self.pts.data_ptr() if k == self.iters else None,    # the last forward's points
+                             step=float(k), **common)
+            return
         N.track_update(st, t_in=self.t[0].data_ptr(), r_in=self.r[0].data_ptr(), t_out=None, r_out=None, grad_pts=None,
                        pts=self.pts.data_ptr(), step=0.0, **common)
         for k in range(1, self.iters + 1):

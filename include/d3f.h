@@ -184,6 +184,20 @@ typedef struct D3FTrack {
 } D3FTrack;
 int d3f_track_update(const D3FTrack* tp, void* stream);
 
+/* d3f_track_step: one whole Adam iteration of rigid_tracking (reference fusion.py:1643-1665) in ONE launch — what the
+ * four calls above do, with one CTA per point: points from (last_pts, t_in, r_in), the field query of `key` at them, the
+ * loss against src (n_inst*n_pts, C), its gradient through the field back to the points (texels read once, kept in
+ * registers for forward and backward), and, by the last CTA of every instance to finish, the Adam step into
+ * (t_out, r_out).  t->grad_pts is ignored: grad_scratch (n_inst*n_pts,3) receives d loss / d pts.  t->pts (nullable)
+ * receives the points this launch evaluated.  arrivals: n_inst uint32 counters, zero before the first call (every launch
+ * leaves them zero).  loss_terms as in d3f_track_loss_grad.
+ * Supported (d3f_track_step_supported() != 0): V <= 4, float32 key, C % 4 == 0, C <= 1024, strides multiples of 4,
+ * 16-byte aligned map and src; D3F_EINVAL otherwise — use the four-call iteration. */
+int d3f_track_step_supported(const D3FObs* obs, const D3FKey* key);
+int d3f_track_step(const D3FObs* obs, const D3FKey* key, const float* src, const D3FTrack* t, float dist_w,
+                   float* grad_scratch, uint32_t* arrivals, float* loss_terms,
+                   uint32_t flags, float mu, void* stream);
+
 /* Fused PCA projection of a descriptor field: y = (x - mean) @ components^T, the
  * sklearn.decomposition.PCA.transform the reference applies on the host to eval's
  * 'dino_feats' (reference fusion.py:1386-1392, weights from pca_model/*.pkl).

@@ -99,8 +99,8 @@ def test_tracker_graph_replay_equals_eager_and_recovers_pose():
 
 @pytest.mark.gpu
 def test_fused_tracker_follows_the_torch_autograd_loop():
-    """FusedRigidTracker (four launches per Adam iteration, analytic pose gradient) against RigidTracker (torch autograd
-    around the same two field kernels): same trajectory with the reference's hyper-parameters (lr 0.01, reg_w 1,
+    """FusedRigidTracker (one launch per Adam iteration, and its four-launch form; analytic pose gradient) against
+    RigidTracker (torch autograd around the same two field kernels): same trajectory with the reference's hyper-parameters (lr 0.01, reg_w 1,
     dist_w 100) and with the gentle ones, rotation included; graph replay == eager launches; frame after frame."""
     from d3fields_b200.tracking import FusedRigidTracker
     from util import make_fusion
@@ -116,27 +116,75 @@ def test_fused_tracker_follows_the_torch_autograd_loop():
     R = so3_exp_map(w)
     c = pts.mean(dim=1, keepdim=True)
     moved = torch.bmm(pts - c, R) + c - shift[:, None, :]
-    for kw in (dict(lr=0.001, reg_w=0.0), dict(lr=0.01, reg_w=1.0), dict(lr=0.003, reg_w=0.1, dist_w=10.0)):
+    cases = [(kw, single) for single in (True, False)
+             for kw in (dict(lr=0.001, reg_w=0.0), dict(lr=0.01, reg_w=1.0), dict(lr=0.003, reg_w=0.1, dist_w=10.0))]
+    for kw, single in cases:
         ref = RigidTracker(f, I, P, 256, iters=60, graph=False, **kw).track(src, moved)
-        fe = FusedRigidTracker(f, I, P, 256, iters=60, graph=False, **kw)
-        fg = FusedRigidTracker(f, I, P, 256, iters=60, graph=True, **kw)
+        fe = FusedRigidTracker(f, I, P, 256, iters=60, graph=False, single_launch=single, **kw)
+        fg = FusedRigidTracker(f, I, P, 256, iters=60, graph=True, single_launch=single, **kw)
         a, b = fe.track(src, moved), fg.track(src, moved)
+        assert fe.launches_per_iteration == (1 if single else 4)
         assert torch.equal(a['t'], b['t']) and torch.equal(a['log_r'], b['log_r']) and torch.equal(a['match_pts'], b['match_pts'])
         # Adam moves every parameter by ~lr per step whatever the gradient's scale, so near the optimum two float32
         # implementations of the same gradient jitter apart by a fraction of lr: the bar is relative to the step and to lr
+        # (measured: up to 0.35 lr in log_r with the weak dist_w = 10 / reg_w = 0.1 pull; the sharp check of the kernels
+        # is the one-iteration comparison in the next test and the fp64 backward test)
         step = max(float((ref['t']).abs().max()), 1e-3)
-        assert (b['t'] - ref['t']).abs().max() <= 0.02 * step + 0.2 * kw['lr'], (kw, b['t'], ref['t'])
-        assert (b['log_r'] - ref['log_r']).abs().max() <= 0.02 * max(float(ref['log_r'].abs().max()), 1e-3) + 0.2 * kw['lr'], (kw, b['log_r'], ref['log_r'])
-        assert (b['match_pts'] - ref['match_pts']).abs().max() <= 3e-4 + 0.3 * kw['lr']
+        rstep = max(float(ref['log_r'].abs().max()), 1e-3)
+        dt, dr = float((b['t'] - ref['t']).abs().max()), float((b['log_r'] - ref['log_r']).abs().max())
+        dp = float((b['match_pts'] - ref['match_pts']).abs().max())
+        print(kw, 'single' if single else 'four', 'max |dt|', dt, 'of', step, ' max |dlog_r|', dr, 'of', rstep, ' max |dpts|', dp)
+        assert dt <= 0.02 * step + 0.5 * kw['lr'], (kw, b['t'], ref['t'])
+        assert dr <= 0.02 * rstep + 0.5 * kw['lr'], (kw, b['log_r'], ref['log_r'])
+        assert dp <= 3e-4 + 0.5 * kw['lr']
         # the reported loss is the reference's (fusion.py:1651-1653) at the last forward's points.  (It cannot be compared
         # with the other tracker's value tightly: |feat - src| over 256 channels changes by ~150 per metre, so 3e-4 m of
-        # trajectory jitter is 0.05 of loss.)
+        # trajectory jitter is 0.05 of loss: the bar on the two trackers' losses carries that term.)
         o = f.eval(b['match_pts'].reshape(-1, 3), return_names=['dino_feats'])
         want = tracking_loss(o, src, torch.zeros(1, 3, device=DEV), torch.zeros(1, 3, device=DEV), reg_w=0.0,
                              dist_w=kw.get('dist_w', 100.0))
         assert abs(float(b['data_loss']) - float(want)) <= 1e-4 * abs(float(want)) + 1e-6
-        assert abs(float(b['loss']) - float(ref['loss'])) <= 0.25 * abs(float(ref['loss']))
-        print(kw, 'max |dt|', float((b['t'] - ref['t']).abs().max()), 'of', step, ' max |dlog_r|', float((b['log_r'] - ref['log_r']).abs().max()),
-              ' loss', float(b['loss']), float(ref['loss']))
+        assert abs(float(b['loss']) - float(ref['loss'])) <= 0.25 * abs(float(ref['loss'])) + 200.0 * dp
+        print('   loss', float(b['loss']), float(ref['loss']))
         c2 = fg.track(src, moved)                          # second frame: same graph, restarted state
         assert torch.equal(c2['t'], b['t'])
+
+
+@pytest.mark.gpu
+def test_single_launch_iteration_matches_the_four_launch_iteration():
+    """d3f_track_step against d3f_eval + d3f_track_loss_grad + d3f_eval_backward + d3f_track_update on the same state:
+    after ONE iteration, d loss / d pts, the per-point loss terms and the evaluated points agree to float32 rounding
+    (the two differ only in the order of the channel reductions); the Adam moments — linear in the pose gradient — too.
+    Points no camera sees and a map narrower than the CTA (C = 64 < 1024) are in the mix; counters are left at zero."""
+    from d3fields_b200.tracking import FusedRigidTracker
+    from util import make_fusion
+    DEV = 'cuda:0'
+    for C, (h, w) in ((256, (24, 32)), (64, (30, 40)), (1024, (12, 16))):
+        sc = _trackable_scene(4, 240, 320, h, w, C)
+        f = make_fusion(sc, DEV)
+        I, P = 3, 70
+        pts = torch.from_numpy(_surface_points(I, P, 11)).to(DEV)
+        pts[1, :5] += 5.0                                  # out of every frustum: valid_mask False, zero gradient
+        src = f.eval(pts.reshape(-1, 3), return_names=['dino_feats'])['dino_feats']
+        moved = pts + torch.tensor([0.004, -0.003, 0.002], device=DEV)
+        one = FusedRigidTracker(f, I, P, C, iters=1, graph=False, single_launch=True)
+        four = FusedRigidTracker(f, I, P, C, iters=1, graph=False, single_launch=False)
+        a, b = one.track(src, moved), four.track(src, moved)
+        assert one.launches_per_iteration == 1 and four.launches_per_iteration == 4
+        assert torch.equal(a['match_pts'], b['match_pts'])
+        scale = float(four.grad_pts.abs().max())
+        assert scale > 0
+        assert (one.grad_pts - four.grad_pts).abs().max() <= 2e-4 * scale, (C, (one.grad_pts - four.grad_pts).abs().max(), scale)
+        assert torch.allclose(one.loss_terms, four.loss_terms, rtol=1e-5, atol=1e-7)
+        assert (one.grad_pts.reshape(I, P, 3)[1, :5] == 0).all()
+        for x, y in ((one.m_t, four.m_t), (one.m_r, four.m_r)):
+            assert (x - y).abs().max() <= 2e-4 * float(y.abs().max()) + 1e-9
+        assert torch.allclose(a['t'], b['t'], atol=1e-6) and torch.allclose(a['log_r'], b['log_r'], atol=1e-6)
+        assert int(one.arrivals.abs().sum()) == 0
+        # many iterations in a graph: the counters hand over from launch to launch
+        g1 = FusedRigidTracker(f, I, P, C, iters=40, graph=True, single_launch=True, lr=0.001, reg_w=0.0)
+        g4 = FusedRigidTracker(f, I, P, C, iters=40, graph=True, single_launch=False, lr=0.001, reg_w=0.0)
+        r1, r4 = g1.track(src, moved), g4.track(src, moved)
+        assert (r1['t'] - r4['t']).abs().max() <= 0.25 * 0.001 + 0.02 * float(r4['t'].abs().max())
+        assert torch.equal(g1.track(src, moved)['t'], r1['t'])           # replay is deterministic
+        assert int(g1.arrivals.abs().sum()) == 0
