@@ -99,3 +99,33 @@ def test_integration_stub_matches_the_struct_layouts():
     key = re.sub(r'/\*.*?\*/', '', key, flags=re.S)
     names = re.findall(r'\b([a-zA-Z_]+)\s*(?:,|;)', key)
     assert names == [n for n, _ in _native.D3FKey._fields_], names
+
+
+def test_track_step_eligibility_and_validation_without_gpu():
+    """d3f_track_step_supported is host logic: the one-launch tracking iteration takes V <= 4 and a float32 map with
+    C % 4 == 0, C <= 1024, strides multiples of 4 and a 16-byte aligned base; everything else must say no (the tracker then
+    uses the four-launch iteration), and d3f_track_step itself must refuse it before any CUDA call."""
+    F32, U8 = 0, 1
+    ok = lambda V, key: _native.track_step_supported(V, 480, 640, 16, 16, 16, key)
+    assert ok(4, (256, F32, 48, 64, 1024))
+    assert ok(1, (256, F32, 48, 64, 4))
+    assert ok(4, (256, F32, 48, 64, 256, None, (48 * 80 * 256, 80 * 256, 256)))       # a padded map
+    assert not ok(5, (256, F32, 48, 64, 1024))                                       # more views than register slots
+    assert not ok(4, (256, F32, 48, 64, 1028))                                       # wider than the CTA
+    assert not ok(4, (256, F32, 48, 64, 6))                                          # not float4 rows
+    assert not ok(4, (256, U8, 48, 64, 64))                                          # byte maps
+    assert not ok(4, (260, F32, 48, 64, 64))                                         # 4-byte aligned base only
+    assert not ok(4, (256, F32, 48, 64, 64, None, (48 * 64 * 64 + 2, 64 * 64, 64)))  # stride not a multiple of 4
+    lib = _native.load()
+    with pytest.raises(_native.D3FError):
+        _native.track_step(5, 480, 640, 16, 16, 16, (256, F32, 48, 64, 1024), 16, 100.0, 16, 16, None, 0, 0.02, 0,
+                           t_in=16, r_in=16, t_out=32, r_out=32, m_t=16, v_t=16, m_r=16, v_r=16, last_pts=16,
+                           grad_pts=None, pts=None, n_inst=1, n_pts=10, step=1.0, lr=0.01, beta1=0.9, beta2=0.999,
+                           eps=1e-8, reg_w=1.0)
+    assert b'track_step' in lib.d3f_last_error()
+    with pytest.raises(_native.D3FError):                                            # outputs aliasing the inputs
+        _native.track_step(4, 480, 640, 16, 16, 16, (256, F32, 48, 64, 1024), 16, 100.0, 16, 16, None, 0, 0.02, 0,
+                           t_in=16, r_in=16, t_out=16, r_out=32, m_t=16, v_t=16, m_r=16, v_r=16, last_pts=16,
+                           grad_pts=None, pts=None, n_inst=1, n_pts=10, step=1.0, lr=0.01, beta1=0.9, beta2=0.999,
+                           eps=1e-8, reg_w=1.0)
+    assert b'alias' in lib.d3f_last_error()
