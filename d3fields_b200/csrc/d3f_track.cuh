@@ -56,7 +56,7 @@ struct StepView {
 };
 
 // MINB: resident CTAs per SM the register budget is cut for — 2 (105 registers, no spills; 296 CTAs in flight) or
-// 3 (80 registers, nine spilled words; 444 in flight: the reference's 4 objects x 100 points fit in one wave)
+// 3 (80 registers, twenty spilled words; 444 in flight: the reference's 4 objects x 100 points fit in one wave)
 template <bool RECIP, int MINB>
 __global__ void __launch_bounds__(STEP_THREADS, MINB)
 track_step_kernel(const TrackStepParams sp) {

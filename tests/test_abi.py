@@ -76,6 +76,16 @@ def test_kernel_resource_contract():
         wide = re.search(r'field_tile_kernelILb[01]ELi\d+ELb1ELb[01]ELi[0148]EEE', name) is not None
         assert int(st) == 0 and int(ld) == 0, f'{name}: spills'
         assert int(regs) <= (128 if wide else 64), f'{name}: {regs} registers'
+    # the one-launch tracking iteration keeps 16 texel rows (64 registers) per thread: 2 CTAs of 256 threads per SM without
+    # spilling, and a 3-CTA budget (<= 85 registers) that may spill a few words
+    steps = re.findall(r"Function properties for (\S*track_step_kernelILb[01]ELi([23])\S*)\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                       r"(\d+) bytes spill loads\nptxas info\s*: Used (\d+) registers", log)
+    assert len(steps) == 4, steps
+    for name, minb, stack, st, ld, regs in steps:
+        if minb == '2':
+            assert int(st) == 0 and int(ld) == 0 and int(regs) <= 128, (name, st, ld, regs)
+        else:
+            assert int(regs) <= 85 and int(st) <= 128 and int(ld) <= 128, (name, st, ld, regs)
     sass = subprocess.run(['cuobjdump', '-sass', build.LIB_PATH], capture_output=True, text=True).stdout
     tile = sass[sass.index('field_tile_kernelILb0ELi0ELb1ELb0ELi4'):]
     tile = tile[:tile.index('Function :', 10)] if 'Function :' in tile[10:] else tile
